@@ -1,0 +1,350 @@
+"""CPU oracle for the flex-flash-attention hot path (TEST INFRASTRUCTURE ONLY).
+
+This file is a plain restatement of the reference's *algorithm* for the path, used as the
+checker in ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs.  Nothing under ``magiattention_b200/`` may import it: the product
+path is the CUDA library and fails loudly without it.
+
+Parity pin: ``tests/golden/*.npz`` hold outputs of the reference's own
+``magi_attention.testing.ref_attn.ref_attn_func`` (run on CPU in the build container by
+``tests/golden/gen_golden.py``); ``tests/test_oracle.py`` checks this oracle against them.
+
+Each function cites the reference code it restates (paths relative to /root/reference).
+All math runs in torch on CPU (fp64 for the ground truth, or the input dtype for the
+"low-precision reference" that the reference's two-sided tolerance rule needs).
+"""
+from __future__ import annotations
+
+import math
+from typing import Sequence
+
+import torch
+
+NEG_INF = float("-inf")
+
+# attn_type_map values — magi_attention/common/enum.py:58-76
+FULL, CAUSAL, INVCAUSAL, BICAUSAL = 0, 1, 2, 3
+
+
+def slice_mask(sq: int, sk: int, attn_type: int) -> torch.Tensor:
+    """Boolean mask of ONE AttnSlice, True = attend.
+
+    Restates magi_attention/utils/_utils.py:834-877 (make_slice_mask_from_ffa_attn_type)
+    in closed form, local coordinates i in [0,sq), j in [0,sk):
+      full: all; causal (bottom-right aligned): j <= i + sk - sq;
+      inv-causal (top-left aligned): j >= i; bi-causal: both.
+    """
+    i = torch.arange(sq).unsqueeze(1)
+    j = torch.arange(sk).unsqueeze(0)
+    m = torch.ones(sq, sk, dtype=torch.bool)
+    if attn_type not in (FULL, CAUSAL, INVCAUSAL, BICAUSAL):
+        raise ValueError(f"Invalid attn_type {attn_type}")
+    if attn_type & 1:
+        m &= j <= i + (sk - sq)
+    if attn_type & 2:
+        m &= j >= i
+    return m
+
+
+def mask_from_slices(
+    q_ranges: Sequence[Sequence[int]],
+    k_ranges: Sequence[Sequence[int]],
+    attn_type_map: Sequence[int] | None,
+    total_q: int,
+    total_k: int,
+) -> torch.Tensor:
+    """Dense boolean mask [total_q, total_k] from FFA slice metadata.
+
+    Restates magi_attention/utils/_utils.py:880-922 (make_attn_mask_from_ffa_args): each
+    slice's mask is *assigned* into its (q_range x k_range) rectangle; rectangles are
+    area-disjoint by API contract (tests/test_api/test_functools.py:620).
+    """
+    mask = torch.zeros(total_q, total_k, dtype=torch.bool)
+    if attn_type_map is None:
+        attn_type_map = [FULL] * len(q_ranges)
+    for (q0, q1), (k0, k1), t in zip(q_ranges, k_ranges, attn_type_map):
+        if q1 <= q0 or k1 <= k0:
+            continue
+        mask[q0:q1, k0:k1] = slice_mask(q1 - q0, k1 - k0, int(t))
+    return mask
+
+
+def mask_area(q_ranges, k_ranges, attn_type_map) -> int:
+    """Number of unmasked (q,k) pairs — the `area` in FLOPs = 4*area*nhq*d
+    (exps/dist_attn/benchmark/metric.py:30-54). Closed form per slice."""
+    total = 0
+    if attn_type_map is None:
+        attn_type_map = [FULL] * len(q_ranges)
+    for (q0, q1), (k0, k1), t in zip(q_ranges, k_ranges, attn_type_map):
+        sq, sk = q1 - q0, k1 - k0
+        if sq <= 0 or sk <= 0:
+            continue
+        t = int(t)
+        if t == FULL:
+            total += sq * sk
+            continue
+        # per-row [lo, hi): lo = i if inv else 0 ; hi = i + sk - sq + 1 if causal else sk
+        # sum over rows of max(0, min(hi,sk) - max(lo,0)) — O(1) would need case splits; rows loop is fine
+        i = torch.arange(sq, dtype=torch.int64)
+        lo = i if (t & 2) else torch.zeros_like(i)
+        hi = (i + (sk - sq) + 1) if (t & 1) else torch.full_like(i, sk)
+        hi = hi.clamp(max=sk)
+        lo = lo.clamp(min=0)
+        total += int((hi - lo).clamp(min=0).sum())
+    return total
+
+
+def _expand_kv(x: torch.Tensor, rep: int) -> torch.Tensor:
+    # GQA: repeat each kv head `rep` times — testing/ref_attn.py:487-493
+    return x.repeat_interleave(rep, dim=1) if rep > 1 else x
+
+
+def attn_fwd(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    mask: torch.Tensor,
+    softmax_scale: float | None = None,
+    high_precision: bool = True,
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """O [tq,hq,d] (q dtype) and LSE [tq,hq] fp32 (natural log).
+
+    Restates testing/ref_attn.py:522-569 (_ref_attn_torch_impl_mainprocess_offline) with
+    the safe_lse / safe_softmax handling of fully-masked rows (functional/utils.py:38-104):
+    S = Q K^T * scale + bias; LSE = logsumexp(S); P = exp(S - LSE) cast to q dtype; O = P V;
+    rows with no unmasked key give O = 0, LSE = -inf.  ``high_precision`` computes in fp64
+    (ref_attn.py:715-719), else in the input dtype (the "low-precision reference").
+    """
+    org = q.dtype
+    tq, hq, d = q.shape
+    hk = k.shape[1]
+    scale = d ** -0.5 if softmax_scale is None else softmax_scale
+    if high_precision:
+        q, k, v = q.double(), k.double(), v.double()
+    k = _expand_kv(k, hq // hk)
+    v = _expand_kv(v, hq // hk)
+    qh = q.permute(1, 0, 2)  # [h, tq, d]
+    kt = k.permute(1, 2, 0)  # [h, d, tk]
+    vh = v.permute(1, 0, 2)
+    s = qh @ kt * scale
+    s = s.to(torch.float64 if high_precision else torch.float32)
+    s = s.masked_fill(~mask.unsqueeze(0), NEG_INF)
+    dead = (s == NEG_INF).all(dim=-1, keepdim=True)
+    lse = torch.logsumexp(s, dim=-1, keepdim=True).masked_fill(dead, NEG_INF)
+    p = torch.exp(torch.where(s == NEG_INF, s, s - torch.where(dead, torch.zeros_like(lse), lse)))
+    p = p.masked_fill(dead, 0.0).to(qh.dtype)
+    out = p @ vh
+    out = out.permute(1, 0, 2).contiguous().to(org)
+    lse = lse.squeeze(-1).t().contiguous()
+    lse = lse.to(torch.float64 if org == torch.float64 else torch.float32)
+    return out, lse
+
+
+def attn_bwd(
+    do: torch.Tensor,
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    out: torch.Tensor,
+    lse: torch.Tensor,
+    mask: torch.Tensor,
+    softmax_scale: float | None = None,
+    high_precision: bool = True,
+) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(dQ, dK, dV) for a *partial* attention given the GLOBAL out/lse.
+
+    Restates functional/sdpa.py:270-327 (sdpa_bwd_recalc_fwd + sdpa_bwd_calc with delta):
+      P = exp(S - LSE); dV = P^T dO; dP = dO V^T; delta = rowsum(O * dO);
+      dS = P * (dP - delta) * scale; dQ = dS K; dK = dS^T Q.
+    Because LSE and O are the global ones, partial grads over disjoint key sets add exactly —
+    the property the CP runtime relies on (functional/dist_attn.py:3561).
+    """
+    org = q.dtype
+    tq, hq, d = q.shape
+    hk = k.shape[1]
+    rep = hq // hk
+    scale = d ** -0.5 if softmax_scale is None else softmax_scale
+    if high_precision:
+        do, q, k, v, out = do.double(), q.double(), k.double(), v.double(), out.double()
+    cdt = torch.float64 if high_precision else torch.float32
+    ke, ve = _expand_kv(k, rep), _expand_kv(v, rep)
+    qh, kh, vh = q.permute(1, 0, 2), ke.permute(1, 0, 2), ve.permute(1, 0, 2)
+    doh, oh = do.permute(1, 0, 2), out.permute(1, 0, 2)
+    s = (qh @ kh.transpose(-1, -2) * scale).to(cdt)
+    s = s.masked_fill(~mask.unsqueeze(0), NEG_INF)
+    l = lse.t().unsqueeze(-1).to(cdt)  # [h, tq, 1]
+    dead = l == NEG_INF
+    p = torch.exp(torch.where(s == NEG_INF, s, s - torch.where(dead, torch.zeros_like(l), l)))
+    p = p.masked_fill(dead, 0.0).to(qh.dtype)
+    delta = (oh.to(cdt) * doh.to(cdt)).sum(-1, keepdim=True).to(qh.dtype)
+    dv = p.transpose(-1, -2) @ doh
+    dp = doh @ vh.transpose(-1, -2)
+    ds = p * (dp - delta) * scale
+    dq = ds @ kh
+    dk = ds.transpose(-1, -2) @ qh
+    if rep > 1:
+        # sum the q-head group back onto its kv head — functional/sdpa.py:330-345
+        dk = dk.reshape(hk, rep, *dk.shape[1:]).sum(1)
+        dv = dv.reshape(hk, rep, *dv.shape[1:]).sum(1)
+    perm = lambda x: x.permute(1, 0, 2).contiguous().to(org)
+    return perm(dq), perm(dk), perm(dv)
+
+
+def merge_out_lse(
+    out1: torch.Tensor, lse1: torch.Tensor, out2: torch.Tensor, lse2: torch.Tensor
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """LSE-merge of two partial attention results over disjoint key sets.
+
+    Restates functional/utils.py:286-358 (correct_attn_lse / correct_attn_out):
+    lse = max + log1p(exp(min - max)); out = exp(lse1-lse) out1 + exp(lse2-lse) out2;
+    (-inf, -inf) rows stay (0, -inf).
+    """
+    l1, l2 = lse1.double(), lse2.double()
+    mx, mn = torch.maximum(l1, l2), torch.minimum(l1, l2)
+    both_dead = mx == NEG_INF
+    diff = torch.where(both_dead, torch.full_like(mx, NEG_INF), mn - torch.where(both_dead, torch.zeros_like(mx), mx))
+    lse = mx + torch.log1p(torch.exp(diff))
+    lse = lse.masked_fill(both_dead, NEG_INF)
+    safe = torch.where(both_dead, torch.zeros_like(lse), lse)
+    w1 = torch.exp(torch.where(l1 == NEG_INF, l1, l1 - safe)).unsqueeze(-1)
+    w2 = torch.exp(torch.where(l2 == NEG_INF, l2, l2 - safe)).unsqueeze(-1)
+    out = w1 * out1.double() + w2 * out2.double()
+    return out.to(out1.dtype), lse.to(lse1.dtype)
+
+
+def ffa_fwd(q, k, v, q_ranges, k_ranges, attn_type_map, softmax_scale=None, high_precision=True):
+    """flex_flash_attn forward semantics (functional/flex_flash_attn.py:1066) via the dense mask."""
+    mask = mask_from_slices(q_ranges, k_ranges, attn_type_map, q.shape[0], k.shape[0])
+    return attn_fwd(q, k, v, mask, softmax_scale, high_precision)
+
+
+def ffa_bwd(do, q, k, v, out, lse, q_ranges, k_ranges, attn_type_map, softmax_scale=None, high_precision=True):
+    mask = mask_from_slices(q_ranges, k_ranges, attn_type_map, q.shape[0], k.shape[0])
+    return attn_bwd(do, q, k, v, out, lse, mask, softmax_scale, high_precision)
+
+
+# ------------------------------------------------------------------------------------------
+# group collectives — naive single-process semantics of
+# comm/primitive/grpcoll/_group_collective.py:81-205 (group_cast) and :255-408 (group_reduce),
+# as exercised by tests/test_comm/test_group_collective.py (the "naive" comparison impl).
+# ------------------------------------------------------------------------------------------
+def group_cast_ref(
+    inputs: list[torch.Tensor],
+    input_split_sizes: list[list[int]],
+    dst_indices: list[list[list[int]]],
+    src_index: list[list[int]],
+    output_split_sizes: list[list[int]],
+) -> list[torch.Tensor]:
+    """World-level group_cast: rank r's input is split by input_split_sizes[r]; split i goes to
+    every rank in dst_indices[r][i].  Rank r's output is the concatenation of the splits it
+    receives, ordered as src_index[r] lists the source ranks ("stable": splits from the same
+    source keep their relative order)."""
+    world = len(inputs)
+    queues = [[[] for _ in range(world)] for _ in range(world)]  # queues[dst][src] -> list of splits
+    for r in range(world):
+        off = 0
+        for sz, dsts in zip(input_split_sizes[r], dst_indices[r]):
+            chunk = inputs[r][off : off + sz]
+            off += sz
+            for dst in dsts:
+                queues[dst][r].append(chunk)
+    outs = []
+    for r in range(world):
+        taken = [0] * world
+        parts = []
+        for sz, src in zip(output_split_sizes[r], src_index[r]):
+            c = queues[r][src][taken[src]]
+            taken[src] += 1
+            assert c.shape[0] == sz
+            parts.append(c)
+        outs.append(torch.cat(parts, 0) if parts else inputs[r][:0])
+    return outs
+
+
+def group_reduce_ref(
+    inputs: list[torch.Tensor],
+    outputs: list[torch.Tensor],
+    input_split_sizes: list[list[int]],
+    dst_index: list[list[int]],
+    src_indices: list[list[list[int]]],
+    output_split_sizes: list[list[int]],
+) -> list[torch.Tensor]:
+    """World-level group_reduce(sum, acc_reduce=True): the exact transpose of group_cast.  Rank r's
+    input split i goes to rank dst_index[r][i]; rank r's output split j accumulates (sum, fp64 here)
+    the splits received from the ranks in src_indices[r][j], on top of its existing content."""
+    world = len(inputs)
+    queues = [[[] for _ in range(world)] for _ in range(world)]
+    for r in range(world):
+        off = 0
+        for sz, dst in zip(input_split_sizes[r], dst_index[r]):
+            queues[dst][r].append(inputs[r][off : off + sz])
+            off += sz
+    outs = []
+    for r in range(world):
+        out = outputs[r].clone().double()
+        taken = [0] * world
+        off = 0
+        for sz, srcs in zip(output_split_sizes[r], src_indices[r]):
+            for src in srcs:
+                c = queues[r][src][taken[src]]
+                taken[src] += 1
+                assert c.shape[0] == sz
+                out[off : off + sz] += c.double()
+            off += sz
+        outs.append(out.to(outputs[r].dtype))
+    return outs
+
+
+# ------------------------------------------------------------------------------------------
+# tolerance rule — tests/test_attn/test_flex_flash_attn.py:680-738,839-873 and
+# magi_attention/testing/precision.py:33-157
+# ------------------------------------------------------------------------------------------
+NORM_RTOL_RATIO = 2.0  # testing/precision.py:36
+MISMATCH_THRES_RATIO = 2.0
+MAX_MISMATCH_THRES = 0.75
+RTOL = {"out": 0.05, "lse": 1e-3, "dq": 0.3, "dk": 0.15, "dv": 0.05}
+ATOL = 1e-8
+
+
+def _mismatch_ratio(a: torch.Tensor, ref: torch.Tensor, atol: float, rtol: float) -> float:
+    a, ref = a.double(), ref.double()
+    both_inf = torch.isinf(a) & torch.isinf(ref) & (a == ref)
+    bad = (a - ref).abs() > atol + rtol * ref.abs()
+    bad = bad & ~both_inf
+    bad = bad | (torch.isnan(a) != torch.isnan(ref))
+    return float(bad.double().mean()) if bad.numel() else 0.0
+
+
+def _inf_norm(x: torch.Tensor) -> float:
+    x = x.double()
+    x = torch.where(torch.isinf(x), torch.zeros_like(x), x)
+    return float(x.abs().max()) if x.numel() else 0.0
+
+
+def check_close(name: str, test: torch.Tensor, ref_hp: torch.Tensor, ref_lp: torch.Tensor, kind: str) -> dict:
+    """The reference's two-sided rule: ||test-ref64||inf <= 2*||ref_lp-ref64||inf AND
+    mismatch(test) <= max(2*mismatch(ref_lp), small floor) capped at 0.75.
+    Returns a report dict; raises AssertionError on violation."""
+    t, hp, lp = test.double(), ref_hp.double(), ref_lp.double()
+    assert torch.equal(torch.isinf(t), torch.isinf(hp)), f"{name}: -inf pattern differs from oracle"
+    assert not torch.isnan(t).any(), f"{name}: NaN in result"
+    norm_t = _inf_norm(torch.where(torch.isinf(hp), torch.zeros_like(t), t - hp))
+    norm_lp = _inf_norm(torch.where(torch.isinf(hp), torch.zeros_like(lp), lp - hp))
+    rtol = RTOL[kind]
+    mm_t = _mismatch_ratio(t, hp, ATOL, rtol)
+    mm_lp = _mismatch_ratio(lp, hp, ATOL, rtol)
+    thres = min(max(MISMATCH_THRES_RATIO * mm_lp, 1e-4), MAX_MISMATCH_THRES)
+    rep = dict(name=name, norm=norm_t, norm_ref=norm_lp, mismatch=mm_t, mismatch_ref=mm_lp, thres=thres)
+    norm_floor = 1e-6 if kind == "lse" else 0.0
+    assert norm_t <= NORM_RTOL_RATIO * norm_lp + norm_floor, f"{name}: inf-norm {norm_t:.3e} > 2 x {norm_lp:.3e} ({rep})"
+    assert mm_t <= thres, f"{name}: mismatch ratio {mm_t:.3e} > {thres:.3e} ({rep})"
+    return rep
+
+
+def flops_fwd(area: int, nhq: int, d: int) -> float:
+    # exps/dist_attn/benchmark/metric.py:46-48
+    return 4.0 * area * nhq * d
+
+
+def flops_bwd(area: int, nhq: int, d: int) -> float:
+    return 2.5 * flops_fwd(area, nhq, d)

