@@ -1,0 +1,160 @@
+/* b200_ffa.h — C ABI of the B200-native flex-flash-attention library (libb200_ffa.so).
+ *
+ * Drop-in boundary for the reference's native FFA module.  Each entry point names the
+ * reference interface it replaces (paths relative to the MagiAttention repo root):
+ *
+ *   b200_ffa_fwd        <- pybind `mod.fwd(q,k,v,sink?,out?,lse?,...,q_ranges,k_ranges,attn_type_map,
+ *                          ...,softmax_scale,softcap,out_type,sink_layout,sm_margin)`
+ *                          magi_attention/csrc/flexible_flash_attention/fwd_inst_template.jinja:67-138,
+ *                          host glue flex_flash_fwd.hpp:190-383, params flash.h:32-143 (Flash_fwd_params);
+ *                          on B200 it takes the slot of fa4_fwd (magi_attention/functional/fa4.py:128-221).
+ *   b200_ffa_bwd        <- pybind `mod.bwd(dout,q,k,v,sink?,out,dq?,dk?,dv?,dsink?,lse,q_ranges,k_ranges,
+ *                          attn_type_map,...,softmax_scale,softcap,dq_type,dk_type,dv_type,...)`
+ *                          bwd_inst_template.jinja:58-107, flex_flash_bwd.hpp:200-425, flash.h:145-189;
+ *                          B200 slot: fa4_bwd (functional/fa4.py:225-321).
+ *   b200_ffa_*_workspace_bytes <- the per-call workspace allocations the reference makes itself
+ *                          (range_locks / tile semaphore flex_flash_fwd.hpp:299-318; softmax_d / lse_log2
+ *                          flex_flash_bwd.hpp:351-352).  Here the CALLER owns the workspace.
+ *   b200_lse_merge      <- correct_attn_out_lse (magi_attention/functional/utils.py:467-558, Triton).
+ *   b200_range_reduce_sum <- range_reduce(sum) post-process of group_reduce
+ *                          (magi_attention/common/range_op/_range_reduce.py:360).
+ *
+ * Conventions (differences from the pybind module are deliberate and listed in INTEGRATION.md):
+ *   - plain pointers and sizes only; no torch types; all tensors are DEVICE pointers;
+ *   - q/k/v/out/dout/dq/dk/dv are [tokens, heads, head_dim] with head_dim contiguous; strides in ELEMENTS;
+ *   - q_ranges / k_ranges are int32 [num_slices, 2] ([start, end) token spans), attn_type_map int32
+ *     [num_slices] or NULL (= all FULL); 0 full, 1 causal (bottom-right aligned), 2 inv-causal
+ *     (top-left aligned), 3 bi-causal  (magi_attention/common/enum.py:58-76);
+ *   - never allocates, never synchronises, never throws: work is enqueued on `stream`; returns 0 or a
+ *     negative code and b200_ffa_last_error() describes the failure (thread-local string);
+ *   - slices are area-disjoint (reference API contract); q ranges may overlap.
+ */
+#ifndef B200_FFA_H_
+#define B200_FFA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200_stream_t; /* cudaStream_t */
+
+enum b200_dtype { B200_F16 = 0, B200_BF16 = 1, B200_F32 = 2 };
+
+enum b200_status {
+  B200_OK = 0,
+  B200_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+  B200_ERR_WORKSPACE = -2,   /* workspace too small or misaligned */
+  B200_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed */
+  B200_ERR_UNSUPPORTED = -4  /* valid in the reference, not implemented here (e.g. sink, softcap) */
+};
+
+typedef struct {
+  /* inputs */
+  const void* q;               /* [total_q, num_heads_q, head_dim]  f16/bf16 */
+  const void* k;               /* [total_k, num_heads_kv, head_dim] */
+  const void* v;               /* [total_k, num_heads_kv, head_dim] */
+  /* outputs (caller-allocated) */
+  void* out;                   /* [total_q, num_heads_q, head_dim], out_dtype */
+  float* lse;                  /* [total_q, num_heads_q] fp32, natural log */
+  /* slice metadata (device) */
+  const int32_t* q_ranges;     /* [num_slices, 2] */
+  const int32_t* k_ranges;     /* [num_slices, 2] */
+  const int32_t* attn_type_map;/* [num_slices] or NULL */
+  int32_t num_slices;
+  /* shapes */
+  int32_t total_q, total_k, num_heads_q, num_heads_kv, head_dim;
+  int64_t q_stride_t, q_stride_h;     /* element strides */
+  int64_t k_stride_t, k_stride_h;
+  int64_t v_stride_t, v_stride_h;
+  int64_t o_stride_t, o_stride_h;
+  int64_t lse_stride_t, lse_stride_h;
+  float softmax_scale;
+  float softcap;               /* must be 0 */
+  int32_t dtype;               /* b200_dtype of q/k/v */
+  int32_t out_dtype;           /* b200_dtype of out: same as dtype, or B200_F32 */
+  /* accumulate != 0: (out, lse) hold a previous partial result over a disjoint key set and are merged
+   * in place with this call's result (reference: passing out_/lse to _flex_flash_attn_forward,
+   * functional/flex_flash_attn.py:334-456; the CP stage merge dist_attn.py:3126-3131).
+   * accumulate == 0: out/lse are overwritten; uncovered rows get out = 0, lse = -inf. */
+  int32_t accumulate;
+  int32_t sm_margin;           /* SMs to leave free for concurrent comm kernels */
+  void* workspace;             /* >= b200_ffa_fwd_workspace_bytes(), 256-byte aligned */
+  size_t workspace_bytes;
+} b200_ffa_fwd_params;
+
+typedef struct {
+  const void* dout;            /* [total_q, num_heads_q, head_dim] */
+  const void* q;
+  const void* k;
+  const void* v;
+  const void* out;             /* GLOBAL (fully merged) forward output, dtype == `dtype` */
+  const float* lse;            /* GLOBAL lse [total_q, num_heads_q] */
+  /* gradients (caller-allocated). dq is fp32 and is ALWAYS accumulated into (zero it first for a fresh
+   * result; reference: dq passed to _flex_flash_attn_backward, flex_flash_attn.py:594-693).
+   * dk/dv: dkv_dtype; accumulate_dkv != 0 adds into existing contents (fp32 only). */
+  float* dq;                   /* [total_q, num_heads_q, head_dim] fp32 */
+  void* dk;                    /* [total_k, num_heads_kv, head_dim] */
+  void* dv;
+  const int32_t* q_ranges;
+  const int32_t* k_ranges;
+  const int32_t* attn_type_map;
+  int32_t num_slices;
+  int32_t total_q, total_k, num_heads_q, num_heads_kv, head_dim;
+  int64_t q_stride_t, q_stride_h;
+  int64_t k_stride_t, k_stride_h;
+  int64_t v_stride_t, v_stride_h;
+  int64_t o_stride_t, o_stride_h;
+  int64_t do_stride_t, do_stride_h;
+  int64_t dq_stride_t, dq_stride_h;
+  int64_t dk_stride_t, dk_stride_h;
+  int64_t dv_stride_t, dv_stride_h;
+  int64_t lse_stride_t, lse_stride_h;
+  float softmax_scale;
+  float softcap;               /* must be 0 */
+  int32_t dtype;               /* of q/k/v/out/dout */
+  int32_t dkv_dtype;           /* same as dtype, or B200_F32 */
+  int32_t accumulate_dkv;
+  int32_t sm_margin;
+  void* workspace;
+  size_t workspace_bytes;
+} b200_ffa_bwd_params;
+
+/* Library / build identification: "b200_ffa <version> sm_100a". */
+B200_API const char* b200_ffa_version(void);
+/* Description of the last error on the calling thread ("" if none). */
+B200_API const char* b200_ffa_last_error(void);
+
+B200_API size_t b200_ffa_fwd_workspace_bytes(const b200_ffa_fwd_params* p);
+B200_API size_t b200_ffa_bwd_workspace_bytes(const b200_ffa_bwd_params* p);
+
+B200_API int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream);
+B200_API int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream);
+
+/* In-place LSE merge of a second partial attention result into (out, lse):
+ *   lse' = logaddexp(lse, lse2); out' = exp(lse-lse') out + exp(lse2-lse') out2; (-inf,-inf) stays (0,-inf).
+ * out/out2: [rows, heads, dim] with the given dtypes (contiguous), lse/lse2: [rows, heads] fp32. */
+B200_API int b200_lse_merge(void* out, float* lse, const void* out2, const float* lse2, int64_t rows, int32_t heads,
+                   int32_t dim, int32_t out_dtype, int32_t out2_dtype, b200_stream_t stream);
+
+/* dst[dst_ranges[i]] += src[src_ranges[i]] row-span by row-span (fp32 accumulate), row = `row_elems`
+ * contiguous elements.  ranges are int32 [n,2] device arrays; spans i have equal length on both sides. */
+B200_API int b200_range_reduce_sum(void* dst, int32_t dst_dtype, const void* src, int32_t src_dtype,
+                          const int32_t* dst_ranges, const int32_t* src_ranges, int32_t num_ranges,
+                          int64_t row_elems, b200_stream_t stream);
+
+/* Number of kernels the last b200_ffa_fwd / b200_ffa_bwd call on this thread launched (for bench accounting). */
+B200_API int b200_ffa_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_FFA_H_ */

@@ -1,0 +1,147 @@
+// ffa_api.cu — the C ABI declared in include/b200_ffa.h: argument checking, TMA tensor-map encoding,
+// workspace carving and kernel launches.  Mirrors the role of the reference's host glue
+// (csrc/flexible_flash_attention/flex_flash_common.cpp, flex_flash_fwd.hpp:190-383,
+// flex_flash_bwd.hpp:200-425) minus everything torch: no allocation, no sync, no exceptions.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "../../include/b200_ffa.h"
+#include "ffa_args.h"
+#include "ffa_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+typedef CUresult (*EncodeTiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiled_t get_encode() {
+  static EncodeTiled_t fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiled_t)p;
+  }
+  return fn;
+}
+
+// [tokens, heads, 128] 16-bit tensor -> 3-D map (d, h, t), box (64, 1, box_rows), SWIZZLE_128B.
+int make_map_thd(CUtensorMap* m, const void* ptr, int dtype, int tokens, int heads, int64_t stride_t, int64_t stride_h,
+                 int box_rows, const char* what) {
+  EncodeTiled_t enc = get_encode();
+  if (!enc) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (stride_t * 2) % 16 || (stride_h * 2) % 16)
+    return fail(B200_ERR_INVALID, "%s: pointer/strides must be 16-byte aligned", what);
+  cuuint64_t dims[3] = {cuuint64_t(ffa::kHeadDim), cuuint64_t(heads), cuuint64_t(tokens)};
+  cuuint64_t strides[2] = {cuuint64_t(stride_h) * 2, cuuint64_t(stride_t) * 2};
+  cuuint32_t box[3] = {64, 1, cuuint32_t(box_rows)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, dtype == B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, int(r));
+  return 0;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int check_common(int dtype, int hq, int hk, int d, float softcap) {
+  if (dtype != B200_F16 && dtype != B200_BF16) return fail(B200_ERR_INVALID, "dtype must be f16 or bf16");
+  if (d != ffa::kHeadDim) return fail(B200_ERR_UNSUPPORTED, "head_dim %d unsupported (only 128)", d);
+  if (hq <= 0 || hk <= 0 || hq % hk) return fail(B200_ERR_INVALID, "num_heads_q %d must be a multiple of num_heads_kv %d", hq, hk);
+  if (softcap != 0.f) return fail(B200_ERR_UNSUPPORTED, "softcap is not supported");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200_ffa_version(void) { return "b200_ffa 0.1.0 sm_100a"; }
+const char* b200_ffa_last_error(void) { return g_err; }
+int b200_ffa_last_launch_count(void) { return g_launches; }
+
+size_t b200_ffa_fwd_workspace_bytes(const b200_ffa_fwd_params* p) {
+  if (!p) return 0;
+  int n_tiles = (p->total_q + ffa::kFwdTileQ - 1) / ffa::kFwdTileQ;
+  return align_up(ffa::plan_bytes(n_tiles, p->num_slices), 256);
+}
+
+int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
+  g_err[0] = 0;
+  g_launches = 0;
+  if (!p) return fail(B200_ERR_INVALID, "null params");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = check_common(p->dtype, p->num_heads_q, p->num_heads_kv, p->head_dim, p->softcap)) return rc;
+  if (p->out_dtype != p->dtype && p->out_dtype != B200_F32) return fail(B200_ERR_INVALID, "out_dtype must equal dtype or be f32");
+  if (p->total_q < 0 || p->total_k < 0 || p->num_slices < 0) return fail(B200_ERR_INVALID, "negative size");
+  if (p->total_q == 0) return 0;
+  if (!p->q || !p->out || !p->lse) return fail(B200_ERR_INVALID, "null q/out/lse");
+  if (p->num_slices > 0 && (!p->q_ranges || !p->k_ranges)) return fail(B200_ERR_INVALID, "null ranges");
+  if (p->total_k > 0 && (!p->k || !p->v)) return fail(B200_ERR_INVALID, "null k/v");
+  const size_t o_align = p->out_dtype == B200_F32 ? 16 : 16;
+  if ((reinterpret_cast<uintptr_t>(p->out) % o_align) || (p->o_stride_t * (p->out_dtype == B200_F32 ? 4 : 2)) % 16 ||
+      (p->o_stride_h * (p->out_dtype == B200_F32 ? 4 : 2)) % 16)
+    return fail(B200_ERR_INVALID, "out pointer/strides must be 16-byte aligned");
+  const int n_tiles = (p->total_q + ffa::kFwdTileQ - 1) / ffa::kFwdTileQ;
+  const size_t need = b200_ffa_fwd_workspace_bytes(p);
+  if (!p->workspace || p->workspace_bytes < ffa::plan_entries_off(n_tiles) * sizeof(int) + sizeof(int) ||
+      (reinterpret_cast<uintptr_t>(p->workspace) & 255))
+    return fail(B200_ERR_WORKSPACE, "workspace too small (%zu < %zu) or not 256-byte aligned", p->workspace_bytes, need);
+
+  ffa::SliceMeta meta{reinterpret_cast<const int2*>(p->q_ranges), reinterpret_cast<const int2*>(p->k_ranges),
+                      p->attn_type_map, p->num_slices};
+  int* plan = static_cast<int*>(p->workspace);
+  const size_t cap_bytes = p->workspace_bytes - ffa::plan_entries_off(n_tiles) * sizeof(int);
+  const int capacity = int(cap_bytes / sizeof(int) > 0x7fffffff ? 0x7fffffff : cap_bytes / sizeof(int));
+  cudaError_t e = ffa::launch_plan(true, meta, n_tiles, capacity, plan, stream);
+  if (e != cudaSuccess) return fail(B200_ERR_CUDA, "plan launch: %s", cudaGetErrorString(e));
+  ++g_launches;
+
+  CUtensorMap tmQ, tmK, tmV;
+  if (int rc = make_map_thd(&tmQ, p->q, p->dtype, p->total_q, p->num_heads_q, p->q_stride_t, p->q_stride_h, 128, "q")) return rc;
+  // k/v may legally be empty (total_k == 0): point the maps at q so encoding succeeds; no block is ever loaded.
+  const bool kv_empty = p->total_k == 0;
+  if (int rc = make_map_thd(&tmK, kv_empty ? p->q : p->k, p->dtype, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
+                            kv_empty ? p->q_stride_t : p->k_stride_t, kv_empty ? p->q_stride_h : p->k_stride_h, 128, "k")) return rc;
+  if (int rc = make_map_thd(&tmV, kv_empty ? p->q : p->v, p->dtype, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
+                            kv_empty ? p->q_stride_t : p->v_stride_t, kv_empty ? p->q_stride_h : p->v_stride_h, 128, "v")) return rc;
+
+  ffa::FwdArgs a{};
+  a.meta = meta;
+  a.plan = plan;
+  a.out = p->out;
+  a.lse = p->lse;
+  a.total_q = p->total_q;
+  a.total_k = p->total_k;
+  a.num_heads_q = p->num_heads_q;
+  a.num_heads_kv = p->num_heads_kv;
+  a.n_tiles = n_tiles;
+  a.o_stride_t = p->o_stride_t;
+  a.o_stride_h = p->o_stride_h;
+  a.lse_stride_t = p->lse_stride_t;
+  a.lse_stride_h = p->lse_stride_h;
+  a.scale = p->softmax_scale;
+  a.accumulate = p->accumulate;
+  e = ffa::launch_fwd(p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream);
+  if (e != cudaSuccess) return fail(B200_ERR_CUDA, "fwd launch: %s", cudaGetErrorString(e));
+  ++g_launches;
+  return 0;
+}
+
+}  // extern "C"

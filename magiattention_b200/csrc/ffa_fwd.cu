@@ -1,0 +1,466 @@
+// ffa_fwd.cu — flex-flash-attention FORWARD for sm_100a (tcgen05 + TMEM + TMA).
+//
+// Replaces the reference's Hopper-only FFA forward (csrc/flexible_flash_attention/
+// flash_fwd_kernel_sm90.h:189-455, mainloop_fwd_sm90_tma_gmma_ws.hpp, epilogue_fwd.hpp) and the FA4
+// CuTe-DSL kernel it falls back to on Blackwell (flash_attn/cute/flash_fwd_sm100.py).  Design:
+//
+//  * One CTA owns a 256-row q tile of one head (two 128-row MMA tiles that share every K/V block) and
+//    walks ALL slices touching those rows (tile->slice CSR from ffa_plan.cu).  Rows are therefore
+//    reduced across slices in registers/TMEM: no global locks, no fp32 atomics on O, no LSE-merge pass.
+//  * Warp roles (384 threads): warps 0-3 softmax of tile 0, warps 4-7 softmax of tile 1, warp 8 lane 0
+//    issues every tcgen05.mma, warp 9 lane 0 issues every TMA load.  Softmax thread i owns row i of its
+//    tile (TMEM lane i): row max / row sum need no shuffles.
+//  * TMEM (512 cols): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P (16-bit) overwrites the
+//    first 64 columns of its S.  MMA order per kv block:  PV0(prev) S0(cur) PV1(prev) S1(cur)  so the
+//    softmax of one tile always overlaps two MMAs of the other.
+//  * K and V blocks (128 x 128, two SWIZZLE_128B TMA boxes each) stream through a 5-deep ring; Q tiles
+//    are loaded once.
+//  * Online softmax in base 2 with lazy rescaling: the reference max only moves when it would grow by
+//    more than 2^8, so the O correction (TMEM load-scale-store) is rare and done by the softmax warps
+//    themselves; it is safe because S(cur) completing implies PV(prev) completed (in-order tensor pipe).
+//  * Epilogue normalises, optionally LSE-merges into a previous partial (out, lse) — the CP stage merge
+//    the reference does with a separate Triton pass (functional/utils.py:467-558) — and stores rows.
+#include <cuda.h>
+#include <cmath>
+#include <type_traits>
+#include "ffa_common.cuh"
+#include "ffa_args.h"
+#include "ffa_kernels.h"
+#include "sm100.cuh"
+
+namespace ffa {
+using namespace sm100;
+
+namespace fwd {
+constexpr int kThreads = 384;
+constexpr int kStages = 5;
+constexpr uint32_t kTileBytes = 128 * 128 * 2;  // one 128x128 16-bit operand tile (2 boxes)
+constexpr uint32_t kBoxBytes = kTileBytes / 2;
+constexpr uint32_t kSmemQ = 0;
+constexpr uint32_t kSmemKV = 2 * kTileBytes;
+constexpr uint32_t kSmemBar = kSmemKV + kStages * kTileBytes;
+constexpr uint32_t kSmemBytes = kSmemBar + 256;
+// barrier indices
+constexpr int kBarQ = 0, kBarFull = 1, kBarEmpty = kBarFull + kStages, kBarS = kBarEmpty + kStages, kBarP = kBarS + 2,
+              kBarO = kBarP + 2, kNumBars = kBarO + 2;
+static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
+constexpr uint32_t kTmemS = 0, kTmemO = 256;
+constexpr float kRescaleThreshold = 8.0f;
+}  // namespace fwd
+
+
+// Per-slice geometry for one forward CTA tile (rows [R0, R0+256)) and for one of its two MMA tiles.
+struct CtaGeom {
+  int c_min, nblk;
+  __device__ __forceinline__ bool init(const Slice& s, int R0) {
+    int r_lo = max(s.q0, R0), r_hi = min(s.q1, R0 + kFwdTileQ);
+    int c_max;
+    if (!col_hull(s, r_lo, r_hi, c_min, c_max)) return false;
+    nblk = (c_max - c_min + kBlockN - 1) / kBlockN;
+    return true;
+  }
+};
+struct TileGeom {
+  int ct_min, ct_max, full_lo, full_hi;
+  bool act, rows_full;
+  __device__ __forceinline__ void init(const Slice& s, int t0) {
+    int a = max(s.q0, t0), b = min(s.q1, t0 + kBlockM);
+    ct_min = ct_max = full_lo = full_hi = 0;
+    act = col_hull(s, a, b, ct_min, ct_max);
+    rows_full = (a == t0) && (b == t0 + kBlockM);
+    if (act) {
+      full_lo = s.lo(b - 1);
+      full_hi = min(s.hi(a), s.k1);
+    }
+  }
+  __device__ __forceinline__ bool active(int bs) const { return act && (bs + kBlockN > ct_min) && (bs < ct_max); }
+  __device__ __forceinline__ bool full(int bs) const { return rows_full && full_lo <= bs && bs + kBlockN <= full_hi; }
+};
+
+template <bool kBF16, bool kOutF32>
+__global__ void __launch_bounds__(fwd::kThreads, 1)
+ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const FwdArgs args) {
+  using namespace fwd;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemBar + kNumBars * 8);
+  const uint32_t bar0 = smem_base + kSmemBar;
+  auto bar = [&](int i) -> uint32_t { return bar0 + uint32_t(i) * 8u; };
+
+  const int tid = threadIdx.x;
+  const int wid = tid >> 5;
+  const int lane = tid & 31;
+
+  // ---- work decode: kv-head major, then tile (heaviest = highest index first), then q head in group
+  const int G = args.num_heads_q / args.num_heads_kv;
+  const int per_kvh = args.n_tiles * G;
+  const int hk = blockIdx.x / per_kvh;
+  const int rem = blockIdx.x - hk * per_kvh;
+  const int tile = args.n_tiles - 1 - rem / G;
+  const int hq = hk * G + rem % G;
+  const int R0 = tile * kFwdTileQ;
+
+  if (tid == 0) {
+    if (smem_base & 1023u) {
+      printf("ffa_fwd: dynamic smem not 1024-aligned\n");
+      __trap();
+    }
+    mbar_init(bar(kBarQ), 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(bar(kBarFull + i), 1);
+      mbar_init(bar(kBarEmpty + i), 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar(kBarS + t), 1);
+      mbar_init(bar(kBarP + t), 128);
+      mbar_init(bar(kBarO + t), 1);
+    }
+    fence_barrier_init();
+  }
+  if (wid == 8) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  if (wid == 9 && lane == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (wid < 8) {
+    // =========================== softmax warpgroups ===========================
+    setmaxnreg_inc<208>();
+    const int t = wid >> 2;                        // MMA tile 0/1
+    const int row_in_tile = (wid & 3) * 32 + lane;  // TMEM lane
+    const int row = R0 + t * kBlockM + row_in_tile;
+    const uint32_t lane_off = uint32_t((wid & 3) * 32) << 16;
+    const uint32_t tS = tmem + lane_off + kTmemS + t * 128;
+    const uint32_t tO = tmem + lane_off + kTmemO + t * 128;
+    const float sl2 = args.scale * 1.4426950408889634f;
+
+    float m_ref = -INFINITY, l_sum = 0.f;
+    uint32_t n_act = 0;
+    SliceCursor cur;
+    cur.init(args.meta, args.plan, tile);
+    Slice sl;
+    CtaGeom g;
+    TileGeom tg;
+    while (cur.next(sl)) {
+      if (!g.init(sl, R0)) continue;
+      tg.init(sl, R0 + t * kBlockM);
+      const bool row_in = (row >= sl.q0) && (row < sl.q1);
+      const int lo_r = row_in ? sl.lo(row) : 0;
+      const int hi_r = row_in ? min(sl.hi(row), sl.k1) : 0;  // empty range when row not in slice
+      for (int b = 0; b < g.nblk; ++b) {
+        const int bs = g.c_min + b * kBlockN;
+        if (!tg.active(bs)) continue;
+        mbar_wait(bar(kBarS + t), n_act & 1);
+        tc_fence_after();
+        uint32_t sr[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[c * 32]));
+        tc_wait_ld();
+        if (!tg.full(bs)) {
+          const int lo_rel = lo_r - bs, hi_rel = hi_r - bs;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            int lo_c = min(max(lo_rel - c * 32, 0), 32), hi_c = min(max(hi_rel - c * 32, 0), 32);
+            uint32_t m_hi = hi_c >= 32 ? 0xffffffffu : ((1u << hi_c) - 1u);
+            uint32_t m_lo = lo_c >= 32 ? 0xffffffffu : ((1u << lo_c) - 1u);
+            uint32_t bits = m_hi & ~m_lo;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!((bits >> i) & 1u)) sr[c * 32 + i] = 0xff800000u;  // -inf
+          }
+        }
+        float mb = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 128; ++i) mb = fmaxf(mb, __uint_as_float(sr[i]));
+        const float m_new = fmaxf(m_ref, mb);
+        const bool upd = (m_new - m_ref) * sl2 > kRescaleThreshold;  // NaN (-inf - -inf) compares false
+        float corr = 1.f;
+        if (upd) {
+          corr = (m_ref == -INFINITY) ? 0.f : ex2((m_ref - m_new) * sl2);
+          m_ref = m_new;
+          l_sum *= corr;
+        }
+        if (n_act > 0 && __any_sync(0xffffffffu, upd)) {
+          // rescale O (PV of the previous block has completed: its commit preceded S(cur)'s)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tO + c * 32, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+            tmem_st32(tO + c * 32, o);
+          }
+        }
+        const float mneg = (m_ref == -INFINITY) ? 0.f : -m_ref * sl2;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pr[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float p0 = ex2(fmaf(__uint_as_float(sr[64 * c + 2 * i]), sl2, mneg));
+            float p1 = ex2(fmaf(__uint_as_float(sr[64 * c + 2 * i + 1]), sl2, mneg));
+            l_sum += p0 + p1;
+            pr[i] = pack2<kBF16>(p0, p1);
+          }
+          tmem_st32(tS + c * 32, pr);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar(kBarP + t));
+        ++n_act;
+      }
+    }
+
+    // ------------------------------- epilogue -------------------------------
+    const bool row_ok = row < args.total_q;
+    const bool dead = (n_act == 0) || (m_ref == -INFINITY) || !(l_sum > 0.f);
+    float lse_new = dead ? -INFINITY : fmaf(m_ref, args.scale, __logf(l_sum));
+    float w_new = dead ? 0.f : 1.f / l_sum;
+    float w_old = 0.f;
+    float* lse_ptr = args.lse + int64_t(row) * args.lse_stride_t + int64_t(hq) * args.lse_stride_h;
+    bool need_old = false;
+    if (args.accumulate && row_ok) {
+      const float lse_old = *lse_ptr;
+      if (lse_old != -INFINITY) {
+        need_old = true;
+        if (dead) {
+          w_old = 1.f;
+          lse_new = lse_old;
+        } else {
+          const float mx = fmaxf(lse_old, lse_new), mn = fminf(lse_old, lse_new);
+          const float lse_m = mx + log1pf(__expf(mn - mx));
+          w_old = __expf(lse_old - lse_m);
+          w_new *= __expf(lse_new - lse_m);
+          lse_new = lse_m;
+        }
+      }
+    }
+    if (n_act > 0) {
+      mbar_wait(bar(kBarO + t), 0);
+      tc_fence_after();
+    }
+    using OutT = typename std::conditional<kOutF32, float, typename std::conditional<kBF16, __nv_bfloat16, __half>::type>::type;
+    OutT* orow = reinterpret_cast<OutT*>(args.out) + int64_t(row) * args.o_stride_t + int64_t(hq) * args.o_stride_h;
+    const bool skip_store = !row_ok || (args.accumulate && dead);  // accumulate + nothing new: keep old
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float o[32];
+      if (n_act > 0) {
+        uint32_t r[32];
+        tmem_ld32(tO + c * 32, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]) * w_new;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+      }
+      if (dead) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+      }
+      if (!skip_store) {
+        if constexpr (kOutF32) {
+          float4* dst = reinterpret_cast<float4*>(orow + c * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 x = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            if (need_old) {
+              float4 y = dst[i];
+              x.x = fmaf(w_old, y.x, x.x); x.y = fmaf(w_old, y.y, x.y);
+              x.z = fmaf(w_old, y.z, x.z); x.w = fmaf(w_old, y.w, x.w);
+            }
+            dst[i] = x;
+          }
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = o[8 * i + j];
+            if (need_old) {
+              uint4 y = dst[i];
+              const uint32_t yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float lo, hi;
+                if constexpr (kBF16) {
+                  lo = __uint_as_float(yw[j] << 16);
+                  hi = __uint_as_float(yw[j] & 0xffff0000u);
+                } else {
+                  __half2 h2 = *reinterpret_cast<const __half2*>(&yw[j]);
+                  lo = __low2float(h2);
+                  hi = __high2float(h2);
+                }
+                x[2 * j] = fmaf(w_old, lo, x[2 * j]);
+                x[2 * j + 1] = fmaf(w_old, hi, x[2 * j + 1]);
+              }
+            }
+            uint4 pk;
+            pk.x = pack2<kBF16>(x[0], x[1]);
+            pk.y = pack2<kBF16>(x[2], x[3]);
+            pk.z = pack2<kBF16>(x[4], x[5]);
+            pk.w = pack2<kBF16>(x[6], x[7]);
+            dst[i] = pk;
+          }
+        }
+      }
+    }
+    if (!skip_store) *lse_ptr = lse_new;
+  } else {
+    setmaxnreg_dec<80>();
+    if (wid == 8) { if (lane == 0) {
+      // =========================== MMA issuer ===========================
+      constexpr uint32_t idesc_s = make_idesc(kBF16, false, false, 128, 128);
+      constexpr uint32_t idesc_pv = make_idesc(kBF16, false, true, 128, 128);
+      constexpr uint64_t desc_v_hi = desc_mnmajor(kBoxBytes);
+      const uint32_t sQ = smem_base + kSmemQ, sKV = smem_base + kSmemKV;
+      uint32_t n_act[2] = {0, 0};       // active blocks issued so far per tile
+      bool has_prev[2] = {false, false};
+      uint32_t prev_load[2] = {0, 0};   // ring load index of the V block of the pending PV
+      uint32_t pend = 0;                // outstanding PV users per ring buffer, 4 bits each
+      uint32_t blk = 0;                 // kv block counter (ring: K = 2*blk, V = 2*blk+1)
+      bool q_ready = false;
+
+      auto issue_pv = [&](int t) {
+        // P_t of the pending block is in TMEM once the softmax warps arrive
+        mbar_wait(bar(kBarP + t), (n_act[t] - 1) & 1);
+        const uint32_t li = prev_load[t], buf = li % kStages;
+        mbar_wait(bar(kBarFull + buf), (li / kStages) & 1);
+        tc_fence_after();
+        const uint32_t sV = sKV + buf * kTileBytes;
+        const uint32_t tP = tmem + kTmemS + t * 128, tOt = tmem + kTmemO + t * 128;
+#pragma unroll
+        for (uint32_t kk = 0; kk < 8; ++kk)
+          mma_ts(tOt, tP + kk * 8, smem_desc(desc_v_hi, sV + kk * 2048), idesc_pv, (n_act[t] > 1 || kk > 0) ? 1u : 0u);
+        pend -= 1u << (4 * buf);
+        if (((pend >> (4 * buf)) & 15u) == 0) tc_commit(bar(kBarEmpty + buf));
+        has_prev[t] = false;
+      };
+
+      SliceCursor cur;
+      cur.init(args.meta, args.plan, tile);
+      Slice sl;
+      CtaGeom g;
+      TileGeom tg0, tg1;
+      while (cur.next(sl)) {
+        if (!g.init(sl, R0)) continue;
+        tg0.init(sl, R0);
+        tg1.init(sl, R0 + kBlockM);
+        for (int b = 0; b < g.nblk; ++b, ++blk) {
+          const int bs = g.c_min + b * kBlockN;
+          const bool a0 = tg0.active(bs), a1 = tg1.active(bs);
+          if (!q_ready) {
+            mbar_wait(bar(kBarQ), 0);
+            q_ready = true;
+          }
+          const uint32_t lk = 2 * blk, kbuf = lk % kStages, lv = lk + 1, vbuf = lv % kStages;
+          mbar_wait(bar(kBarFull + kbuf), (lk / kStages) & 1);
+          tc_fence_after();
+          pend = (pend & ~(15u << (4 * vbuf))) | (((a0 ? 1u : 0u) + (a1 ? 1u : 0u)) << (4 * vbuf));
+          const uint32_t sK = sKV + kbuf * kTileBytes;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (has_prev[t]) issue_pv(t);
+            if (t == 0 ? a0 : a1) {
+              const uint32_t tSt = tmem + kTmemS + t * 128;
+#pragma unroll
+              for (uint32_t kk = 0; kk < 8; ++kk) {
+                const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+                mma_ss(tSt, smem_desc(DESC_KMAJOR, sQ + t * kTileBytes + off), smem_desc(DESC_KMAJOR, sK + off), idesc_s,
+                       kk > 0 ? 1u : 0u);
+              }
+              tc_commit(bar(kBarS + t));
+              has_prev[t] = true;
+              prev_load[t] = lv;
+              ++n_act[t];
+            }
+          }
+          tc_commit(bar(kBarEmpty + kbuf));            // K block free once both S MMAs retire
+          if (((pend >> (4 * vbuf)) & 15u) == 0) tc_commit(bar(kBarEmpty + vbuf));  // V block nobody needs
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        if (has_prev[t]) issue_pv(t);
+        if (n_act[t] > 0) tc_commit(bar(kBarO + t));
+      }
+    } __syncwarp(); } else if (wid == 9) { if (lane == 0) {
+      // =========================== TMA producer ===========================
+      const uint32_t sQ = smem_base + kSmemQ, sKV = smem_base + kSmemKV;
+      uint32_t blk = 0;
+      bool q_loaded = false;
+      SliceCursor cur;
+      cur.init(args.meta, args.plan, tile);
+      Slice sl;
+      CtaGeom g;
+      while (cur.next(sl)) {
+        if (!g.init(sl, R0)) continue;
+        if (!q_loaded) {
+          mbar_arrive_expect_tx(bar(kBarQ), 2 * kTileBytes);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            tma_load_3d(sQ + t * kTileBytes, &tmQ, bar(kBarQ), 0, hq, R0 + t * kBlockM);
+            tma_load_3d(sQ + t * kTileBytes + kBoxBytes, &tmQ, bar(kBarQ), 64, hq, R0 + t * kBlockM);
+          }
+          q_loaded = true;
+        }
+        for (int b = 0; b < g.nblk; ++b, ++blk) {
+          const int bs = g.c_min + b * kBlockN;
+#pragma unroll
+          for (int which = 0; which < 2; ++which) {
+            const uint32_t li = 2 * blk + which, buf = li % kStages;
+            mbar_wait(bar(kBarEmpty + buf), ((li / kStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(bar(kBarFull + buf), kTileBytes);
+            const CUtensorMap* tm = which == 0 ? &tmK : &tmV;
+            tma_load_3d(sKV + buf * kTileBytes, tm, bar(kBarFull + buf), 0, hk, bs);
+            tma_load_3d(sKV + buf * kTileBytes + kBoxBytes, tm, bar(kBarFull + buf), 64, hk, bs);
+          }
+        }
+      }
+    } __syncwarp(); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 8) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------------------
+template <bool kBF16, bool kOutF32>
+static cudaError_t launch_one(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                              const FwdArgs& a, int grid, cudaStream_t stream) {
+  auto kern = ffa_fwd_kernel<kBF16, kOutF32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<grid, fwd::kThreads, fwd::kSmemBytes, stream>>>(tmQ, tmK, tmV, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fwd(bool bf16, bool out_f32, const CUtensorMap& tmQ, const CUtensorMap& tmK,
+                       const CUtensorMap& tmV, const FwdArgs& a, cudaStream_t stream) {
+  const int grid = a.n_tiles * a.num_heads_q;
+  if (grid == 0) return cudaSuccess;
+  if (bf16) return out_f32 ? launch_one<true, true>(tmQ, tmK, tmV, a, grid, stream)
+                           : launch_one<true, false>(tmQ, tmK, tmV, a, grid, stream);
+  return out_f32 ? launch_one<false, true>(tmQ, tmK, tmV, a, grid, stream)
+                 : launch_one<false, false>(tmQ, tmK, tmV, a, grid, stream);
+}
+
+}  // namespace ffa
