@@ -1,0 +1,24 @@
+"""User-facing API (mirror of magi_attention/api/__init__.py)."""
+from ..functional.flex_flash_attn import flex_flash_attn_func  # noqa: F401
+from .functools import (  # noqa: F401
+    compute_pad_size,
+    infer_attn_mask_from_cu_seqlens,
+    infer_attn_mask_from_sliding_window,
+    infer_varlen_mask_from_batch,
+    pad_at_dim,
+    squash_batch_dim,
+    unpad_at_dim,
+)
+from .magi_attn_interface import (  # noqa: F401
+    calc_attn,
+    clear_cache,
+    dispatch,
+    get_most_recent_key,
+    get_position_ids,
+    get_runtime_mgr,
+    magi_attn_flex_dispatch,
+    magi_attn_flex_key,
+    magi_attn_varlen_dispatch,
+    magi_attn_varlen_key,
+    undispatch,
+)

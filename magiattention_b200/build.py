@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static", "-Wno-deprecated-gpu-targets"]
     subprocess.check_call(cmd)
     with open(stamp, "w") as f:
         f.write(dig)

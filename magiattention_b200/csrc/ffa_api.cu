@@ -144,4 +144,102 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   return 0;
 }
 
+
+static inline int bwd_tq_ld(int total_q) { return (total_q + 127) / 128 * 128 + 128; }
+
+size_t b200_ffa_bwd_workspace_bytes(const b200_ffa_bwd_params* p) {
+  if (!p) return 0;
+  const int n_tiles = (p->total_k + ffa::kBwdTileK - 1) / ffa::kBwdTileK;
+  const size_t plan = align_up(ffa::plan_bytes(n_tiles, p->num_slices), 256);
+  const size_t vec = align_up(size_t(p->num_heads_q) * bwd_tq_ld(p->total_q) * sizeof(float), 256);
+  return plan + 2 * vec;
+}
+
+int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream_) {
+  g_err[0] = 0;
+  g_launches = 0;
+  if (!p) return fail(B200_ERR_INVALID, "null params");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = check_common(p->dtype, p->num_heads_q, p->num_heads_kv, p->head_dim, p->softcap)) return rc;
+  if (p->dkv_dtype != p->dtype && p->dkv_dtype != B200_F32) return fail(B200_ERR_INVALID, "dkv_dtype must equal dtype or be f32");
+  if (p->accumulate_dkv && p->dkv_dtype != B200_F32) return fail(B200_ERR_INVALID, "accumulate_dkv requires fp32 dk/dv");
+  if (p->total_q < 0 || p->total_k < 0 || p->num_slices < 0) return fail(B200_ERR_INVALID, "negative size");
+  if (p->total_q == 0 && p->total_k == 0) return 0;
+  if (p->total_q > 0 && (!p->q || !p->dout || !p->out || !p->lse || !p->dq)) return fail(B200_ERR_INVALID, "null q/dout/out/lse/dq");
+  if (p->total_k > 0 && (!p->k || !p->v || !p->dk || !p->dv)) return fail(B200_ERR_INVALID, "null k/v/dk/dv");
+  if (p->num_slices > 0 && (!p->q_ranges || !p->k_ranges)) return fail(B200_ERR_INVALID, "null ranges");
+  if (p->total_k == 0) return 0;  // no keys: dq gets no contribution, nothing to write
+  const int esz = p->dkv_dtype == B200_F32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(p->dk) & 15) || (reinterpret_cast<uintptr_t>(p->dv) & 15) || (p->dk_stride_t * esz) % 16 ||
+      (p->dk_stride_h * esz) % 16 || (p->dv_stride_t * esz) % 16 || (p->dv_stride_h * esz) % 16)
+    return fail(B200_ERR_INVALID, "dk/dv pointers/strides must be 16-byte aligned");
+  if (p->total_q > 0 && ((reinterpret_cast<uintptr_t>(p->dq) & 15) || p->dq_stride_t % 4 || p->dq_stride_h % 4))
+    return fail(B200_ERR_INVALID, "dq pointer/strides must be 16-byte aligned");
+  if (p->total_q > 0 && ((reinterpret_cast<uintptr_t>(p->out) & 7) || (reinterpret_cast<uintptr_t>(p->dout) & 7) || p->o_stride_t % 4 ||
+                         p->o_stride_h % 4 || p->do_stride_t % 4 || p->do_stride_h % 4))
+    return fail(B200_ERR_INVALID, "out/dout pointers/strides must be 8-byte aligned");
+
+  const int n_tiles = (p->total_k + ffa::kBwdTileK - 1) / ffa::kBwdTileK;
+  const int tq_ld = bwd_tq_ld(p->total_q);
+  const size_t vec = align_up(size_t(p->num_heads_q) * tq_ld * sizeof(float), 256);
+  const size_t need = b200_ffa_bwd_workspace_bytes(p);
+  const size_t min_plan = align_up((ffa::plan_entries_off(n_tiles) + 1) * sizeof(int), 256);
+  if (!p->workspace || (reinterpret_cast<uintptr_t>(p->workspace) & 255) || p->workspace_bytes < 2 * vec + min_plan)
+    return fail(B200_ERR_WORKSPACE, "workspace too small (%zu < %zu) or not 256-byte aligned", p->workspace_bytes, need);
+  char* ws = static_cast<char*>(p->workspace);
+  float* delta = reinterpret_cast<float*>(ws);
+  float* lse2 = reinterpret_cast<float*>(ws + vec);
+  int* plan = reinterpret_cast<int*>(ws + 2 * vec);
+  const size_t plan_bytes_avail = p->workspace_bytes - 2 * vec;
+  const size_t cap = (plan_bytes_avail - ffa::plan_entries_off(n_tiles) * sizeof(int)) / sizeof(int);
+  const int capacity = int(cap > 0x7fffffff ? 0x7fffffff : cap);
+
+  ffa::SliceMeta meta{reinterpret_cast<const int2*>(p->q_ranges), reinterpret_cast<const int2*>(p->k_ranges),
+                      p->attn_type_map, p->num_slices};
+  cudaError_t e = ffa::launch_plan(false, meta, n_tiles, capacity, plan, stream);
+  if (e != cudaSuccess) return fail(B200_ERR_CUDA, "plan launch: %s", cudaGetErrorString(e));
+  ++g_launches;
+  e = ffa::launch_bwd_preprocess(p->dtype == B200_BF16, p->out, p->dout, p->lse, delta, lse2, p->total_q, p->num_heads_q, tq_ld,
+                                 p->o_stride_t, p->o_stride_h, p->do_stride_t, p->do_stride_h, p->lse_stride_t, p->lse_stride_h,
+                                 stream);
+  if (e != cudaSuccess) return fail(B200_ERR_CUDA, "bwd preprocess launch: %s", cudaGetErrorString(e));
+  ++g_launches;
+
+  CUtensorMap tmQ, tmDO, tmK, tmV;
+  const bool q_empty = p->total_q == 0;
+  if (int rc = make_map_thd(&tmQ, q_empty ? p->k : p->q, p->dtype, q_empty ? 1 : p->total_q, q_empty ? p->num_heads_kv : p->num_heads_q,
+                            q_empty ? p->k_stride_t : p->q_stride_t, q_empty ? p->k_stride_h : p->q_stride_h, 128, "q")) return rc;
+  if (int rc = make_map_thd(&tmDO, q_empty ? p->k : p->dout, p->dtype, q_empty ? 1 : p->total_q, q_empty ? p->num_heads_kv : p->num_heads_q,
+                            q_empty ? p->k_stride_t : p->do_stride_t, q_empty ? p->k_stride_h : p->do_stride_h, 128, "dout")) return rc;
+  if (int rc = make_map_thd(&tmK, p->k, p->dtype, p->total_k, p->num_heads_kv, p->k_stride_t, p->k_stride_h, 128, "k")) return rc;
+  if (int rc = make_map_thd(&tmV, p->v, p->dtype, p->total_k, p->num_heads_kv, p->v_stride_t, p->v_stride_h, 128, "v")) return rc;
+
+  ffa::BwdArgs a{};
+  a.meta = meta;
+  a.plan = plan;
+  a.lse2 = lse2;
+  a.delta = delta;
+  a.dq = p->dq;
+  a.dk = p->dk;
+  a.dv = p->dv;
+  a.total_q = p->total_q;
+  a.total_k = p->total_k;
+  a.num_heads_q = p->num_heads_q;
+  a.num_heads_kv = p->num_heads_kv;
+  a.n_tiles = n_tiles;
+  a.tq_ld = tq_ld;
+  a.dq_stride_t = p->dq_stride_t;
+  a.dq_stride_h = p->dq_stride_h;
+  a.dk_stride_t = p->dk_stride_t;
+  a.dk_stride_h = p->dk_stride_h;
+  a.dv_stride_t = p->dv_stride_t;
+  a.dv_stride_h = p->dv_stride_h;
+  a.scale = p->softmax_scale;
+  a.accumulate_dkv = p->accumulate_dkv;
+  e = ffa::launch_bwd(p->dtype == B200_BF16, p->dkv_dtype == B200_F32, tmQ, tmDO, tmK, tmV, a, stream);
+  if (e != cudaSuccess) return fail(B200_ERR_CUDA, "bwd launch: %s", cudaGetErrorString(e));
+  ++g_launches;
+  return 0;
+}
+
 }  // extern "C"

@@ -18,4 +18,21 @@ struct FwdArgs {
   int accumulate;
 };
 
+struct BwdArgs {
+  SliceMeta meta;
+  const int* plan;       // kv-tile -> slice CSR
+  const float* lse2;     // [num_heads_q, tq_ld]  lse * log2(e), +inf for dead / pad rows
+  const float* delta;    // [num_heads_q, tq_ld]  rowsum(O o dO)
+  float* dq;             // fp32, accumulated with red.global.add
+  void* dk;
+  void* dv;
+  int total_q, total_k;
+  int num_heads_q, num_heads_kv;
+  int n_tiles;           // kv tiles
+  int tq_ld;
+  int64_t dq_stride_t, dq_stride_h, dk_stride_t, dk_stride_h, dv_stride_t, dv_stride_h;
+  float scale;
+  int accumulate_dkv;
+};
+
 }  // namespace ffa

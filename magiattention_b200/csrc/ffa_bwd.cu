@@ -1,6 +1,557 @@
-// placeholder; replaced by the tcgen05 backward
+// ffa_bwd.cu — flex-flash-attention BACKWARD for sm_100a (tcgen05 + TMEM + TMA).
+//
+// Replaces the reference's Hopper-only FFA backward (csrc/flexible_flash_attention/
+// flash_bwd_preprocess_kernel.h, flash_bwd_kernel_sm90.h, mainloop_bwd_sm90_tma_gmma_ws.hpp,
+// epilogue_bwd.hpp, flash_bwd_postprocess_kernel.h) and the FA4 CuTe-DSL backward it uses on Blackwell
+// (flash_attn/cute/flash_bwd_sm100.py).  Math as functional/sdpa.py:270-327 with the GLOBAL lse / out:
+//     P = exp2(S*scale*log2e - LSE*log2e)   dV += P^T dO    dP = dO V^T    Delta = rowsum(O o dO)
+//     dS = P o (dP - Delta)                 dK += scale * dS^T Q           dQ += scale * dS K
+//
+//  * preprocess kernel: Delta and LSE*log2e into padded [heads, tq_ld] fp32 rows (dead rows: +inf so P = 0).
+//  * main kernel: one CTA owns a 128-row kv tile of one kv head, keeps dK and dV in TMEM for the whole
+//    loop over (q heads of the GQA group) x (slices touching the tile, kv-tile -> slice CSR) x (128-row q
+//    blocks): no atomics and no zero-fill pass for dK/dV.  Everything is computed TRANSPOSED (kv on the
+//    TMEM lanes) so that P^T and dS^T are directly the TMEM A operands of the dV and dK MMAs:
+//        S^T = K Q^T (SS)   dP^T = V dO^T (SS)   dV += P^T dO (TS)   dK += dS^T Q (TS)   dQ = dS K (SS)
+//    dS^T also goes to shared memory (it is the MN-major A operand of the dQ MMA).  dQ tiles are drained
+//    from TMEM by a dedicated warpgroup and reduced into the fp32 global dq with red.global.add.v4.f32.
+//  * TMEM (512 cols): S^T/P^T [0,128)  dP^T/dS^T/dQ [128,256)  dV [256,384)  dK [384,512).
+//  * warps: 0-7 compute (two warpgroups, each owns 64 q columns of every kv row), 8-11 dQ drain,
+//    12 MMA issuer, 13 TMA producer.  K,V resident; Q (+LSE2, Delta) and dO double-buffered.
+#include <cuda.h>
+#include <cmath>
+#include <type_traits>
 #include "../../include/b200_ffa.h"
-extern "C" {
-size_t b200_ffa_bwd_workspace_bytes(const b200_ffa_bwd_params*) { return 0; }
-int b200_ffa_bwd(const b200_ffa_bwd_params*, b200_stream_t) { return B200_ERR_UNSUPPORTED; }
+#include "ffa_args.h"
+#include "ffa_common.cuh"
+#include "ffa_kernels.h"
+#include "sm100.cuh"
+
+namespace ffa {
+using namespace sm100;
+
+namespace bwd {
+constexpr int kThreads = 512;
+constexpr uint32_t kTileBytes = 128 * 128 * 2;
+constexpr uint32_t kBoxBytes = kTileBytes / 2;
+constexpr uint32_t kSmemK = 0, kSmemV = kTileBytes, kSmemDS = 2 * kTileBytes, kSmemQ = 3 * kTileBytes,
+                   kSmemDO = 5 * kTileBytes, kSmemLse = 7 * kTileBytes, kSmemDelta = kSmemLse + 1024,
+                   kSmemBar = kSmemDelta + 1024, kSmemBytes = kSmemBar + 256;
+constexpr int kBarKV = 0, kBarQFull = 1, kBarQEmpty = 3, kBarDOFull = 5, kBarDOEmpty = 7, kBarS = 9, kBarDP = 10,
+              kBarP = 11, kBarDS = 12, kBarDQ = 13, kBarDrained = 14, kBarDKV = 15, kNumBars = 16;
+constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 384;
+}  // namespace bwd
+
+// -------------------------------------------------------------------------------------------------
+// preprocess: delta[h][r] = sum_d O[r,h,d]*dO[r,h,d];  lse2[h][r] = lse[r,h]*log2(e)  (+inf when dead/pad)
+// -------------------------------------------------------------------------------------------------
+template <bool kBF16>
+__global__ void ffa_bwd_preprocess_kernel(const void* __restrict__ out, const void* __restrict__ dout,
+                                          const float* __restrict__ lse, float* __restrict__ delta,
+                                          float* __restrict__ lse2, int total_q, int num_heads, int tq_ld,
+                                          int64_t o_stride_t, int64_t o_stride_h, int64_t do_stride_t,
+                                          int64_t do_stride_h, int64_t lse_stride_t, int64_t lse_stride_h) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t idx = int64_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int64_t total = int64_t(num_heads) * tq_ld;
+  if (idx >= total) return;
+  const int h = int(idx / tq_ld), r = int(idx % tq_ld);
+  if (r >= total_q) {
+    if (lane == 0) {
+      delta[idx] = 0.f;
+      lse2[idx] = INFINITY;
+    }
+    return;
+  }
+  using T = typename std::conditional<kBF16, __nv_bfloat16, __half>::type;
+  const T* o = reinterpret_cast<const T*>(out) + int64_t(r) * o_stride_t + int64_t(h) * o_stride_h;
+  const T* d = reinterpret_cast<const T*>(dout) + int64_t(r) * do_stride_t + int64_t(h) * do_stride_h;
+  uint2 ov = *reinterpret_cast<const uint2*>(o + lane * 4);
+  uint2 dv = *reinterpret_cast<const uint2*>(d + lane * 4);
+  float acc = 0.f;
+  const uint32_t ow[2] = {ov.x, ov.y}, dw[2] = {dv.x, dv.y};
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float o0, o1, d0, d1;
+    if constexpr (kBF16) {
+      o0 = __uint_as_float(ow[i] << 16); o1 = __uint_as_float(ow[i] & 0xffff0000u);
+      d0 = __uint_as_float(dw[i] << 16); d1 = __uint_as_float(dw[i] & 0xffff0000u);
+    } else {
+      __half2 oh = *reinterpret_cast<const __half2*>(&ow[i]), dh = *reinterpret_cast<const __half2*>(&dw[i]);
+      o0 = __low2float(oh); o1 = __high2float(oh); d0 = __low2float(dh); d1 = __high2float(dh);
+    }
+    acc = fmaf(o0, d0, acc);
+    acc = fmaf(o1, d1, acc);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) {
+    const float l = lse[int64_t(r) * lse_stride_t + int64_t(h) * lse_stride_h];
+    delta[idx] = acc;
+    lse2[idx] = (l == -INFINITY) ? INFINITY : l * 1.4426950408889634f;
+  }
 }
+
+// -------------------------------------------------------------------------------------------------
+// main kernel
+// -------------------------------------------------------------------------------------------------
+// Per-slice geometry for one backward CTA tile (kv rows [C0, C0+128)).
+struct BwdGeom {
+  int c_lo, c_hi, r_min, r_max, r_start, nblk, full_lo, full_hi;
+  bool cols_full;
+  __device__ __forceinline__ bool init(const Slice& s, int C0) {
+    c_lo = max(s.k0, C0);
+    c_hi = min(s.k1, C0 + kBwdTileK);
+    if (!row_hull(s, c_lo, c_hi, r_min, r_max)) return false;
+    r_start = r_min & ~3;  // 16-byte aligned LSE/Delta bulk copies
+    nblk = (r_max - r_start + kBlockM - 1) / kBlockM;
+    cols_full = (c_lo == C0) && (c_hi == C0 + kBwdTileK);
+    full_lo = s.rlo(C0 + kBwdTileK - 1);  // largest first-visible row over the tile's columns
+    full_hi = s.rhi(C0);                  // smallest end row
+    return true;
+  }
+  __device__ __forceinline__ bool full(int rs) const { return cols_full && rs >= full_lo && rs + kBlockM <= full_hi; }
+};
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <bool kBF16, bool kDkvF32>
+__global__ void __launch_bounds__(bwd::kThreads, 1)
+ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+               const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const BwdArgs args) {
+  using namespace bwd;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemBar + kNumBars * 8);
+  const uint32_t bar0 = smem_base + kSmemBar;
+  auto bar = [&](int i) -> uint32_t { return bar0 + uint32_t(i) * 8u; };
+
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int hk = blockIdx.x / args.n_tiles;
+  const int tile = blockIdx.x - hk * args.n_tiles;
+  const int C0 = tile * kBwdTileK;
+  const int G = args.num_heads_q / args.num_heads_kv;
+
+  if (tid == 0) {
+    if (smem_base & 1023u) {
+      printf("ffa_bwd: dynamic smem not 1024-aligned\n");
+      __trap();
+    }
+    for (int i = 0; i < kNumBars; ++i) {
+      uint32_t cnt = 1;
+      if (i == kBarP || i == kBarDS) cnt = 256;
+      if (i == kBarDrained) cnt = 128;
+      mbar_init(bar(i), cnt);
+    }
+    fence_barrier_init();
+  }
+  if (wid == 12) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  if (wid == 13 && lane == 0) {
+    prefetch_tmap(&tmQ);
+    prefetch_tmap(&tmDO);
+    prefetch_tmap(&tmK);
+    prefetch_tmap(&tmV);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (wid < 8) {
+    // ================================ compute warpgroups ================================
+    setmaxnreg_inc<152>();
+    const int half = wid >> 2;                       // which 64 q columns of the block
+    const int krow = (wid & 3) * 32 + lane;          // kv row inside the tile == TMEM lane
+    const int c = C0 + krow;                         // global kv index
+    const uint32_t lane_off = uint32_t((wid & 3) * 32) << 16;
+    const uint32_t tS = tmem + lane_off + kTmemS + half * 64;
+    const uint32_t tDP = tmem + lane_off + kTmemDP + half * 64;
+    const float sl2 = args.scale * 1.4426950408889634f;
+    uint8_t* sds_row = smem + kSmemDS + half * kBoxBytes + krow * 128;
+    const int swz = krow & 7;
+
+    uint32_t it = 0;
+    for (int g = 0; g < G; ++g) {
+      SliceCursor cur;
+      cur.init(args.meta, args.plan, tile);
+      Slice sl;
+      BwdGeom gm;
+      while (cur.next(sl)) {
+        if (!gm.init(sl, C0)) continue;
+        const bool col_in = (c >= sl.k0) && (c < sl.k1);
+        const int rlo_c = col_in ? sl.rlo(c) : 0;
+        const int rhi_c = col_in ? sl.rhi(c) : 0;
+        for (int b = 0; b < gm.nblk; ++b, ++it) {
+          const int rs = gm.r_start + b * kBlockM;
+          const uint32_t st = it & 1;
+          const bool is_full = gm.full(rs);
+          mbar_wait(bar(kBarQFull + st), (it >> 1) & 1);  // LSE2 / Delta of this block are in smem
+          const float* s_lse = reinterpret_cast<const float*>(smem + kSmemLse + st * 512) + half * 64;
+          const float* s_del = reinterpret_cast<const float*>(smem + kSmemDelta + st * 512) + half * 64;
+          mbar_wait(bar(kBarS), it & 1);
+          tc_fence_after();
+          float p[64];
+          // ---- pass 1: P^T = exp2(S^T * sl2 - lse2[q]) -> TMEM (A operand of the dV MMA)
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            uint32_t sr[32];
+            tmem_ld32(tS + ch * 32, sr);
+            tc_wait_ld();
+            uint32_t bits = 0xffffffffu;
+            if (!is_full) {
+              const int q_base = rs + half * 64 + ch * 32;
+              const int lo_c = min(max(rlo_c - q_base, 0), 32), hi_c = min(max(rhi_c - q_base, 0), 32);
+              const uint32_t m_hi = hi_c >= 32 ? 0xffffffffu : ((1u << hi_c) - 1u);
+              const uint32_t m_lo = lo_c >= 32 ? 0xffffffffu : ((1u << lo_c) - 1u);
+              bits = m_hi & ~m_lo;
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 l4 = *reinterpret_cast<const float4*>(s_lse + ch * 32 + j * 4);
+              const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = j * 4 + e;
+                float x = ex2(fmaf(__uint_as_float(sr[i]), sl2, -lv[e]));
+                x = ((bits >> i) & 1u) ? x : 0.f;
+                p[ch * 32 + i] = x;
+              }
+              pk[j * 2] = pack2<kBF16>(p[ch * 32 + j * 4], p[ch * 32 + j * 4 + 1]);
+              pk[j * 2 + 1] = pack2<kBF16>(p[ch * 32 + j * 4 + 2], p[ch * 32 + j * 4 + 3]);
+            }
+            tmem_st16(tS + ch * 16, pk);
+          }
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(bar(kBarP));
+          // ---- pass 2: dS^T = P^T o (dP^T - delta[q]) -> TMEM (A of dK MMA) and smem (A of dQ MMA)
+          mbar_wait(bar(kBarDP), it & 1);
+          tc_fence_after();
+          if (it > 0) mbar_wait(bar(kBarDQ), (it - 1) & 1);  // previous dQ MMA has finished reading sdS
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            uint32_t dr[32];
+            tmem_ld32(tDP + ch * 32, dr);
+            tc_wait_ld();
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 d4 = *reinterpret_cast<const float4*>(s_del + ch * 32 + j * 4);
+              const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+              float ds[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) ds[e] = p[ch * 32 + j * 4 + e] * (__uint_as_float(dr[j * 4 + e]) - dl[e]);
+              pk[j * 2] = pack2<kBF16>(ds[0], ds[1]);
+              pk[j * 2 + 1] = pack2<kBF16>(ds[2], ds[3]);
+            }
+            tmem_st16(tDP + ch * 16, pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int chunk = ch * 4 + j;  // 16-byte chunk (8 q values) inside this thread's 128-byte row
+              *reinterpret_cast<uint4*>(sds_row + ((chunk ^ swz) << 4)) =
+                  make_uint4(pk[j * 4], pk[j * 4 + 1], pk[j * 4 + 2], pk[j * 4 + 3]);
+            }
+          }
+          tc_wait_st();
+          tc_fence_before();
+          fence_proxy_async_smem();
+          mbar_arrive(bar(kBarDS));
+        }
+      }
+    }
+    // ------------------------------- dK / dV epilogue -------------------------------
+    if (it > 0) {
+      mbar_wait(bar(kBarDKV), 0);
+      tc_fence_after();
+    }
+    const bool row_ok = c < args.total_k;
+    using DT = typename std::conditional<kDkvF32, float, typename std::conditional<kBF16, __nv_bfloat16, __half>::type>::type;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {  // 0: dV, 1: dK
+      DT* base = reinterpret_cast<DT*>(which == 0 ? args.dv : args.dk);
+      const int64_t st_t = which == 0 ? args.dv_stride_t : args.dk_stride_t;
+      const int64_t st_h = which == 0 ? args.dv_stride_h : args.dk_stride_h;
+      DT* rowp = base + int64_t(c) * st_t + int64_t(hk) * st_h + half * 64;
+      const float mul = which == 0 ? 1.f : args.scale;
+      const uint32_t tsrc = tmem + lane_off + (which == 0 ? kTmemDV : kTmemDK) + half * 64;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        float x[32];
+        if (it > 0) {
+          uint32_t r[32];
+          tmem_ld32(tsrc + ch * 32, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(r[i]) * mul;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = 0.f;
+        }
+        if (!row_ok) continue;
+        if constexpr (kDkvF32) {
+          float4* dst = reinterpret_cast<float4*>(rowp + ch * 32);
+          if (args.accumulate_dkv) {
+            if (it > 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 y = dst[i];
+                dst[i] = make_float4(y.x + x[4 * i], y.y + x[4 * i + 1], y.z + x[4 * i + 2], y.w + x[4 * i + 3]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+          }
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(rowp + ch * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            dst[i] = make_uint4(pack2<kBF16>(x[8 * i], x[8 * i + 1]), pack2<kBF16>(x[8 * i + 2], x[8 * i + 3]),
+                                pack2<kBF16>(x[8 * i + 4], x[8 * i + 5]), pack2<kBF16>(x[8 * i + 6], x[8 * i + 7]));
+        }
+      }
+    }
+  } else if (wid < 12) {
+    // ================================ dQ drain warpgroup ================================
+    setmaxnreg_dec<96>();
+    const uint32_t lane_off = uint32_t((wid & 3) * 32) << 16;
+    const uint32_t tDQ = tmem + lane_off + kTmemDP;
+    const int qrow_in_blk = (wid & 3) * 32 + lane;
+    uint32_t it = 0;
+    for (int g = 0; g < G; ++g) {
+      const int hq = hk * G + g;
+      SliceCursor cur;
+      cur.init(args.meta, args.plan, tile);
+      Slice sl;
+      BwdGeom gm;
+      while (cur.next(sl)) {
+        if (!gm.init(sl, C0)) continue;
+        for (int b = 0; b < gm.nblk; ++b, ++it) {
+          const int row = gm.r_start + b * kBlockM + qrow_in_blk;
+          const bool live = (row >= gm.r_min) && (row < gm.r_max);  // rows outside the hull hold exact zeros
+          float* dq = args.dq + int64_t(row) * args.dq_stride_t + int64_t(hq) * args.dq_stride_h;
+          mbar_wait(bar(kBarDQ), it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(tDQ + hf * 64, r0);
+            tmem_ld32(tDQ + hf * 64 + 32, r1);
+            tc_wait_ld();
+            if (hf == 1) {
+              tc_fence_before();
+              mbar_arrive(bar(kBarDrained));
+            }
+            if (live) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float* p0 = dq + hf * 64 + i * 4;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p0),
+                             "f"(__uint_as_float(r0[4 * i]) * args.scale), "f"(__uint_as_float(r0[4 * i + 1]) * args.scale),
+                             "f"(__uint_as_float(r0[4 * i + 2]) * args.scale), "f"(__uint_as_float(r0[4 * i + 3]) * args.scale)
+                             : "memory");
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float* p1 = dq + hf * 64 + 32 + i * 4;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p1),
+                             "f"(__uint_as_float(r1[4 * i]) * args.scale), "f"(__uint_as_float(r1[4 * i + 1]) * args.scale),
+                             "f"(__uint_as_float(r1[4 * i + 2]) * args.scale), "f"(__uint_as_float(r1[4 * i + 3]) * args.scale)
+                             : "memory");
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    setmaxnreg_dec<96>();
+    if (wid == 12) {
+      if (lane == 0) {
+        // ================================ MMA issuer ================================
+        constexpr uint32_t id_kk = make_idesc(kBF16, false, false, 128, 128);  // S^T, dP^T : both K-major
+        constexpr uint32_t id_tm = make_idesc(kBF16, false, true, 128, 128);   // dV, dK : A tmem, B MN-major
+        constexpr uint32_t id_mm = make_idesc(kBF16, true, true, 128, 128);    // dQ : A, B MN-major
+        constexpr uint64_t mn_hi = desc_mnmajor(kBoxBytes);
+        const uint32_t sK = smem_base + kSmemK, sV = smem_base + kSmemV, sDS = smem_base + kSmemDS;
+        const uint32_t tS = tmem + kTmemS, tDP = tmem + kTmemDP, tDV = tmem + kTmemDV, tDK = tmem + kTmemDK;
+
+        auto mma_kmajor = [&](uint32_t d, uint32_t a, uint32_t b) {
+#pragma unroll
+          for (uint32_t kk = 0; kk < 8; ++kk) {
+            const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+            mma_ss(d, smem_desc(DESC_KMAJOR, a + off), smem_desc(DESC_KMAJOR, b + off), id_kk, kk > 0 ? 1u : 0u);
+          }
+        };
+        auto mma_tmemA = [&](uint32_t d, uint32_t a_tmem, uint32_t b, bool acc) {
+#pragma unroll
+          for (uint32_t kk = 0; kk < 8; ++kk)
+            mma_ts(d, a_tmem + (kk >> 2) * 64 + (kk & 3) * 8, smem_desc(mn_hi, b + kk * 2048), id_tm, (acc || kk > 0) ? 1u : 0u);
+        };
+
+        // total number of iterations for this CTA (all q heads walk the same slice list)
+        uint32_t per_head = 0;
+        {
+          SliceCursor cur;
+          cur.init(args.meta, args.plan, tile);
+          Slice sl;
+          BwdGeom gm;
+          while (cur.next(sl))
+            if (gm.init(sl, C0)) per_head += gm.nblk;
+        }
+        const uint32_t n_it = per_head * uint32_t(G);
+        if (n_it > 0) {
+          mbar_wait(bar(kBarKV), 0);
+          // prologue: S_0, dP_0
+          mbar_wait(bar(kBarQFull + 0), 0);
+          tc_fence_after();
+          mma_kmajor(tS, sK, smem_base + kSmemQ);
+          tc_commit(bar(kBarS));
+          mbar_wait(bar(kBarDOFull + 0), 0);
+          tc_fence_after();
+          mma_kmajor(tDP, sV, smem_base + kSmemDO);
+          tc_commit(bar(kBarDP));
+          for (uint32_t it = 0; it < n_it; ++it) {
+            const uint32_t st = it & 1, nst = st ^ 1;
+            const uint32_t sQ = smem_base + kSmemQ + st * kTileBytes, sDO = smem_base + kSmemDO + st * kTileBytes;
+            const bool has_next = it + 1 < n_it;
+            // dV += P^T dO
+            mbar_wait(bar(kBarP), it & 1);
+            tc_fence_after();
+            mma_tmemA(tDV, tS, sDO, it > 0);
+            tc_commit(bar(kBarDOEmpty + st));  // dO_it no longer needed once dV retires
+            // S_{it+1} (S region is free after dV in tensor-pipe order)
+            if (has_next) {
+              mbar_wait(bar(kBarQFull + nst), ((it + 1) >> 1) & 1);
+              tc_fence_after();
+              mma_kmajor(tS, sK, smem_base + kSmemQ + nst * kTileBytes);
+              tc_commit(bar(kBarS));
+            }
+            // dK += dS^T Q ; dQ = dS K
+            mbar_wait(bar(kBarDS), it & 1);
+            tc_fence_after();
+            mma_tmemA(tDK, tDP, sQ, it > 0);
+            tc_commit(bar(kBarQEmpty + st));
+#pragma unroll
+            for (uint32_t kk = 0; kk < 8; ++kk)
+              mma_ss(tDP, smem_desc(mn_hi, sDS + kk * 2048), smem_desc(mn_hi, sK + kk * 2048), id_mm, kk > 0 ? 1u : 0u);
+            tc_commit(bar(kBarDQ));
+            // dP_{it+1} once the dQ tile has been drained out of the shared TMEM region
+            if (has_next) {
+              mbar_wait(bar(kBarDrained), it & 1);
+              mbar_wait(bar(kBarDOFull + nst), ((it + 1) >> 1) & 1);
+              tc_fence_after();
+              mma_kmajor(tDP, sV, smem_base + kSmemDO + nst * kTileBytes);
+              tc_commit(bar(kBarDP));
+            }
+          }
+          tc_commit(bar(kBarDKV));
+        }
+      }
+      __syncwarp();
+    } else if (wid == 13) {
+      if (lane == 0) {
+        // ================================ TMA producer ================================
+        bool kv_loaded = false;
+        uint32_t it = 0;
+        for (int g = 0; g < G; ++g) {
+          const int hq = hk * G + g;
+          const float* lse2 = args.lse2 + int64_t(hq) * args.tq_ld;
+          const float* delta = args.delta + int64_t(hq) * args.tq_ld;
+          SliceCursor cur;
+          cur.init(args.meta, args.plan, tile);
+          Slice sl;
+          BwdGeom gm;
+          while (cur.next(sl)) {
+            if (!gm.init(sl, C0)) continue;
+            if (!kv_loaded) {
+              mbar_arrive_expect_tx(bar(kBarKV), 2 * kTileBytes);
+              tma_load_3d(smem_base + kSmemK, &tmK, bar(kBarKV), 0, hk, C0);
+              tma_load_3d(smem_base + kSmemK + kBoxBytes, &tmK, bar(kBarKV), 64, hk, C0);
+              tma_load_3d(smem_base + kSmemV, &tmV, bar(kBarKV), 0, hk, C0);
+              tma_load_3d(smem_base + kSmemV + kBoxBytes, &tmV, bar(kBarKV), 64, hk, C0);
+              kv_loaded = true;
+            }
+            for (int b = 0; b < gm.nblk; ++b, ++it) {
+              const int rs = gm.r_start + b * kBlockM;
+              const uint32_t st = it & 1, ph = (it >> 1) & 1;
+              mbar_wait(bar(kBarQEmpty + st), ph ^ 1);
+              mbar_arrive_expect_tx(bar(kBarQFull + st), kTileBytes + 1024);
+              const uint32_t sQ = smem_base + kSmemQ + st * kTileBytes;
+              tma_load_3d(sQ, &tmQ, bar(kBarQFull + st), 0, hq, rs);
+              tma_load_3d(sQ + kBoxBytes, &tmQ, bar(kBarQFull + st), 64, hq, rs);
+              bulk_load(smem_base + kSmemLse + st * 512, lse2 + rs, 512, bar(kBarQFull + st));
+              bulk_load(smem_base + kSmemDelta + st * 512, delta + rs, 512, bar(kBarQFull + st));
+              mbar_wait(bar(kBarDOEmpty + st), ph ^ 1);
+              mbar_arrive_expect_tx(bar(kBarDOFull + st), kTileBytes);
+              const uint32_t sDO = smem_base + kSmemDO + st * kTileBytes;
+              tma_load_3d(sDO, &tmDO, bar(kBarDOFull + st), 0, hq, rs);
+              tma_load_3d(sDO + kBoxBytes, &tmDO, bar(kBarDOFull + st), 64, hq, rs);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 12) tmem_dealloc(tmem, 512);
+}
+
+// -------------------------------------------------------------------------------------------------
+// host launchers
+// -------------------------------------------------------------------------------------------------
+cudaError_t launch_bwd_preprocess(bool bf16, const void* out, const void* dout, const float* lse, float* delta,
+                                  float* lse2, int total_q, int num_heads, int tq_ld, int64_t o_stride_t,
+                                  int64_t o_stride_h, int64_t do_stride_t, int64_t do_stride_h, int64_t lse_stride_t,
+                                  int64_t lse_stride_h, cudaStream_t stream) {
+  const int64_t total = int64_t(num_heads) * tq_ld;
+  const int wpb = 8;
+  const unsigned blocks = unsigned((total + wpb - 1) / wpb);
+  if (blocks == 0) return cudaSuccess;
+  if (bf16)
+    ffa_bwd_preprocess_kernel<true><<<blocks, wpb * 32, 0, stream>>>(out, dout, lse, delta, lse2, total_q, num_heads, tq_ld,
+                                                                   o_stride_t, o_stride_h, do_stride_t, do_stride_h,
+                                                                   lse_stride_t, lse_stride_h);
+  else
+    ffa_bwd_preprocess_kernel<false><<<blocks, wpb * 32, 0, stream>>>(out, dout, lse, delta, lse2, total_q, num_heads, tq_ld,
+                                                                    o_stride_t, o_stride_h, do_stride_t, do_stride_h,
+                                                                    lse_stride_t, lse_stride_h);
+  return cudaGetLastError();
+}
+
+template <bool kBF16, bool kDkvF32>
+static cudaError_t launch_bwd_one(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK,
+                                  const CUtensorMap& tmV, const BwdArgs& a, int grid, cudaStream_t stream) {
+  auto kern = ffa_bwd_kernel<kBF16, kDkvF32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<grid, bwd::kThreads, bwd::kSmemBytes, stream>>>(tmQ, tmDO, tmK, tmV, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bwd(bool bf16, bool dkv_f32, const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK,
+                       const CUtensorMap& tmV, const BwdArgs& a, cudaStream_t stream) {
+  const int grid = a.n_tiles * a.num_heads_kv;
+  if (grid == 0) return cudaSuccess;
+  if (bf16) return dkv_f32 ? launch_bwd_one<true, true>(tmQ, tmDO, tmK, tmV, a, grid, stream)
+                           : launch_bwd_one<true, false>(tmQ, tmDO, tmK, tmV, a, grid, stream);
+  return dkv_f32 ? launch_bwd_one<false, true>(tmQ, tmDO, tmK, tmV, a, grid, stream)
+                 : launch_bwd_one<false, false>(tmQ, tmDO, tmK, tmV, a, grid, stream);
+}
+
+}  // namespace ffa

@@ -77,21 +77,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (and surface as a CUDA error) instead of
-// hanging the GPU.  try_wait suspends in hardware for a while per attempt, so the
-// bound below is many seconds of real time.
-#ifndef SM100_WAIT_LIMIT
-#define SM100_WAIT_LIMIT (1u << 26)
+// Bounded wait: a protocol bug must trap (and surface as a CUDA error) instead of hanging the
+// GPU.  The bound is wall-clock (%globaltimer, ns), checked every 1024 failed probes.
+#ifndef SM100_WAIT_TIMEOUT_NS
+#define SM100_WAIT_TIMEOUT_NS 4000000000ull
 #endif
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > SM100_WAIT_LIMIT) {
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > SM100_WAIT_TIMEOUT_NS) {
       printf("[sm100] mbarrier timeout: block (%d,%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, bar, parity);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 // ----------------------------------------------------------------------------------

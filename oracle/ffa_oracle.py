@@ -116,6 +116,7 @@ def attn_fwd(
     (ref_attn.py:715-719), else in the input dtype (the "low-precision reference").
     """
     org = q.dtype
+    mask = mask.to(q.device)
     tq, hq, d = q.shape
     hk = k.shape[1]
     scale = d ** -0.5 if softmax_scale is None else softmax_scale
@@ -160,6 +161,7 @@ def attn_bwd(
     the property the CP runtime relies on (functional/dist_attn.py:3561).
     """
     org = q.dtype
+    mask = mask.to(q.device)
     tq, hq, d = q.shape
     hk = k.shape[1]
     rep = hq // hk

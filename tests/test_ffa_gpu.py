@@ -1,0 +1,208 @@
+"""GPU parity tests of the flex-flash-attention kernels (through the C ABI) against the oracle.
+
+Tolerance: the reference's two-sided rule (tests/test_attn/test_flex_flash_attn.py:680-738,839-873):
+  ||x - ref64||_inf <= 2 * ||ref_lowprec - ref64||_inf   and   mismatch ratio (atol 1e-8; rtol out 0.05,
+  lse 1e-3, dq 0.3, dk 0.15, dv 0.05) <= 2x the low-precision reference's own (capped at 0.75).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mask_configs import mask_configs
+from oracle import ffa_oracle as orc
+
+pytestmark = pytest.mark.gpu
+D = 128
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _run_case(qr, kr, ty, T, TK, HQ, HK, dtype, seed=0, check_bwd=True):
+    from magiattention_b200.functional import flex_flash_attn_func
+
+    dev = _dev()
+    torch.manual_seed(seed)
+    q = torch.randn(T, HQ, D, dtype=dtype, device=dev, requires_grad=True)
+    k = torch.randn(TK, HK, D, dtype=dtype, device=dev, requires_grad=True)
+    v = torch.randn(TK, HK, D, dtype=dtype, device=dev, requires_grad=True)
+    do = torch.randn(T, HQ, D, dtype=dtype, device=dev)
+    qr_t = torch.tensor(qr, dtype=torch.int32, device=dev).reshape(-1, 2)
+    kr_t = torch.tensor(kr, dtype=torch.int32, device=dev).reshape(-1, 2)
+    ty_t = torch.tensor(ty, dtype=torch.int32, device=dev)
+    out, meta = flex_flash_attn_func(q, k, v, qr_t, kr_t, ty_t)
+    mask = orc.mask_from_slices(qr, kr, ty, T, TK)
+    qc, kc, vc, doc = (x.detach().cpu() for x in (q, k, v, do))
+    ro, rl = orc.attn_fwd(qc, kc, vc, mask, high_precision=True)
+    lo, ll = orc.attn_fwd(qc, kc, vc, mask, high_precision=False)
+    ro64, _ = orc.attn_fwd(qc.double(), kc.double(), vc.double(), mask, high_precision=True)
+    orc.check_close("out", out.detach().cpu(), ro64, lo, "out")
+    orc.check_close("lse", meta.lse.cpu(), rl, ll, "lse")
+    if not check_bwd:
+        return
+    out.backward(do)
+    ref = orc.attn_bwd(doc, qc.double(), kc.double(), vc.double(), ro64, rl.double(), mask, high_precision=True)
+    lp = orc.attn_bwd(doc, qc, kc, vc, lo, ll, mask, high_precision=False)
+    for name, g, r, l in zip(("dq", "dk", "dv"), (q.grad, k.grad, v.grad), ref, lp):
+        orc.check_close(name, g.cpu(), r, l, name)
+
+
+@pytest.mark.parametrize("cfg", mask_configs(1), ids=[c["name"] for c in mask_configs(1)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_ffa_mask_configs(cfg, dtype):
+    """Every reference mask family (tests/mask_configs.py), GQA 2:1, fwd + bwd."""
+    T = cfg["seqlen"]
+    _run_case(cfg["q_ranges"], cfg["k_ranges"], cfg["types"], T, T, 2, 1, dtype)
+
+
+@pytest.mark.parametrize("hq,hk", [(1, 1), (4, 4), (8, 2)])
+def test_ffa_head_configs(hq, hk):
+    _run_case([[0, 700]], [[0, 900]], [1], 700, 900, hq, hk, torch.bfloat16)
+
+
+def test_ffa_ragged_and_empty():
+    # ragged sizes, an empty slice, tq not a tile multiple, tk < one block
+    _run_case([[0, 77], [77, 77], [100, 333]], [[0, 50], [3, 9], [10, 50]], [0, 0, 2], 333, 50, 2, 2, torch.bfloat16)
+    # no slices at all: out = 0, lse = -inf, grads = 0
+    _run_case([], [], [], 130, 70, 2, 1, torch.bfloat16)
+
+
+def test_ffa_golden_masks_full_size():
+    """The golden-fixture masks (pinned to the reference's ref_attn_func at d=16 on CPU) re-run on the GPU
+    kernels at d=128 against the same oracle."""
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    assert files
+    for f in files[:6]:
+        g = np.load(f)
+        T = int(g["q"].shape[0])
+        _run_case(g["q_ranges"].tolist(), g["k_ranges"].tolist(), g["types"].tolist(), T, T, 2, 1, torch.bfloat16,
+                  check_bwd=False)
+
+
+def test_forward_accumulate_matches_lse_merge():
+    """Accumulator semantics (reference tests/test_attn/test_flex_flash_attn.py:362-540): passing (out, lse)
+    in must equal correct_attn_out_lse of the separate results."""
+    from magiattention_b200.functional import _flex_flash_attn_forward
+
+    dev = _dev()
+    torch.manual_seed(3)
+    T, TK, H = 600, 1000, 2
+    q = torch.randn(T, H, D, dtype=torch.bfloat16, device=dev)
+    k = torch.randn(TK, H, D, dtype=torch.bfloat16, device=dev)
+    v = torch.randn(TK, H, D, dtype=torch.bfloat16, device=dev)
+    mk = lambda r: torch.tensor(r, dtype=torch.int32, device=dev).reshape(-1, 2)
+    qr1, kr1, ty1 = mk([[0, 600]]), mk([[0, 400]]), torch.tensor([0], dtype=torch.int32, device=dev)
+    qr2, kr2, ty2 = mk([[100, 500]]), mk([[400, 1000]]), torch.tensor([1], dtype=torch.int32, device=dev)
+    scale = D ** -0.5
+    o1, m1 = _flex_flash_attn_forward(q, k, v, None, "sh", None, None, qr1, kr1, ty1, scale, 0.0, torch.float32)
+    o2, m2 = _flex_flash_attn_forward(q, k, v, None, "sh", None, None, qr2, kr2, ty2, scale, 0.0, torch.float32)
+    ref_o, ref_l = orc.merge_out_lse(o1.cpu(), m1.lse.cpu(), o2.cpu(), m2.lse.cpu())
+    oa, la = o1.clone(), m1.lse.clone()
+    _flex_flash_attn_forward(q, k, v, None, "sh", oa, la, qr2, kr2, ty2, scale, 0.0, torch.float32)
+    torch.testing.assert_close(oa.cpu(), ref_o, atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(la.cpu(), ref_l, atol=1e-5, rtol=1e-4)
+    # random accumulators, as the reference test does
+    o_acc = torch.randn(T, H, D, dtype=torch.float32, device=dev)
+    l_acc = torch.randn(T, H, dtype=torch.float32, device=dev)
+    ref_o, ref_l = orc.merge_out_lse(o_acc.cpu(), l_acc.cpu(), o2.cpu(), m2.lse.cpu())
+    _flex_flash_attn_forward(q, k, v, None, "sh", o_acc, l_acc, qr2, kr2, ty2, scale, 0.0, torch.float32)
+    torch.testing.assert_close(o_acc.cpu(), ref_o, atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(l_acc.cpu(), ref_l, atol=1e-5, rtol=1e-4)
+    # and the standalone merge kernel (correct_attn_out_lse replacement)
+    from magiattention_b200 import _lib
+    ob, lb = o1.clone(), m1.lse.clone()
+    _lib.lse_merge(ob, lb, o2, m2.lse)
+    ref_o, ref_l = orc.merge_out_lse(o1.cpu(), m1.lse.cpu(), o2.cpu(), m2.lse.cpu())
+    torch.testing.assert_close(ob.cpu(), ref_o, atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(lb.cpu(), ref_l, atol=1e-5, rtol=1e-4)
+
+
+def test_backward_accumulates_dq_and_dkv():
+    """bwd with given fp32 dq / dk / dv adds into them (reference :541-643); partial grads over disjoint key
+    sets (global lse) sum to the full gradient."""
+    from magiattention_b200.functional import _flex_flash_attn_backward, _flex_flash_attn_forward
+
+    dev = _dev()
+    torch.manual_seed(4)
+    T, H = 512, 2
+    q, k, v, do = (torch.randn(T, H, D, dtype=torch.bfloat16, device=dev) for _ in range(4))
+    mk = lambda r: torch.tensor(r, dtype=torch.int32, device=dev).reshape(-1, 2)
+    ty = torch.tensor([1], dtype=torch.int32, device=dev)
+    scale = D ** -0.5
+    full_q, full_k = mk([[0, T]]), mk([[0, T]])
+    out, meta = _flex_flash_attn_forward(q, k, v, None, "sh", None, None, full_q, full_k, ty, scale, 0.0, None)
+    dq, dk, dv, _ = _flex_flash_attn_backward(do, q, k, v, None, "sh", out, meta.lse, None, None, None, None,
+                                              full_q, full_k, ty, scale, 0.0)
+    # split: keys [0,200) are FULL for rows >= 200 and causal for rows < 200 ; keys [200,T) causal for rows >= 200
+    qa, ka, ta = mk([[0, 200], [200, T]]), mk([[0, 200], [0, 200]]), torch.tensor([1, 0], dtype=torch.int32, device=dev)
+    qb, kb, tb = mk([[200, T]]), mk([[200, T]]), torch.tensor([1], dtype=torch.int32, device=dev)
+    dq2 = torch.zeros_like(dq)
+    dk2 = torch.zeros_like(dk)
+    dv2 = torch.zeros_like(dv)
+    _flex_flash_attn_backward(do, q, k, v, None, "sh", out, meta.lse, dq2, dk2, dv2, None, qa, ka, ta, scale, 0.0)
+    _flex_flash_attn_backward(do, q, k, v, None, "sh", out, meta.lse, dq2, dk2, dv2, None, qb, kb, tb, scale, 0.0)
+    torch.testing.assert_close(dq2, dq, atol=2e-3, rtol=1e-3)
+    torch.testing.assert_close(dk2, dk, atol=2e-3, rtol=1e-3)
+    torch.testing.assert_close(dv2, dv, atol=2e-3, rtol=1e-3)
+
+
+def test_error_behaviour():
+    from magiattention_b200.functional import flex_flash_attn_func
+
+    dev = _dev()
+    q = torch.randn(64, 2, D, dtype=torch.bfloat16, device=dev)
+    r = torch.tensor([[0, 64]], dtype=torch.int32, device=dev)
+    with pytest.raises(AssertionError):
+        flex_flash_attn_func(q, q, q, r, r, None, softcap=1.0)
+    with pytest.raises(AssertionError):
+        flex_flash_attn_func(q, q, q, r, r, None, sink=torch.zeros(1, 2, device=dev))
+    with pytest.raises(RuntimeError):
+        q64 = torch.randn(64, 2, 64, dtype=torch.bfloat16, device=dev)
+        flex_flash_attn_func(q64, q64, q64, r, r, None)
+    with pytest.raises(RuntimeError):
+        flex_flash_attn_func(q.cpu(), q.cpu(), q.cpu(), r.cpu(), r.cpu(), None)
+
+
+@pytest.mark.slow
+def test_full_size_properties_c2_like():
+    """BASELINE config-2-like size (64K packed varlen, causal + sliding window): size-independent properties —
+    linearity in V, lse invariance to V, and row-block agreement with the oracle on a sampled document."""
+    from magiattention_b200.functional import flex_flash_attn_func
+
+    dev = _dev()
+    torch.manual_seed(5)
+    T, H = 65536, 4
+    lens = [4096, 12288, 1024, 16384, 8192, 3000, 5192, 15360]
+    assert sum(lens) == T
+    qr, kr, ty = [], [], []
+    pos = 0
+    for i, n in enumerate(lens):
+        if i % 2 == 0:
+            qr.append([pos, pos + n]); kr.append([pos, pos + n]); ty.append(1)
+        else:
+            w = 1024
+            qr.append([pos, pos + w]); kr.append([pos, pos + w]); ty.append(1)
+            qr.append([pos + w, pos + n]); kr.append([pos, pos + n]); ty.append(3)
+        pos += n
+    mk = lambda r: torch.tensor(r, dtype=torch.int32, device=dev).reshape(-1, 2)
+    q, k, v, v2 = (torch.randn(T, H, D, dtype=torch.bfloat16, device=dev) for _ in range(4))
+    qr_t, kr_t, ty_t = mk(qr), mk(kr), torch.tensor(ty, dtype=torch.int32, device=dev)
+    o1, m1 = flex_flash_attn_func(q, k, v, qr_t, kr_t, ty_t)
+    o2, m2 = flex_flash_attn_func(q, k, v2, qr_t, kr_t, ty_t)
+    o3, m3 = flex_flash_attn_func(q, k, (v.float() + v2.float()).to(torch.bfloat16), qr_t, kr_t, ty_t)
+    assert torch.equal(m1.lse, m2.lse)
+    torch.testing.assert_close(o3.float(), o1.float() + o2.float(), atol=6e-2, rtol=5e-2)
+    # oracle on document 2 (1024 rows, causal) and the head of document 3's band
+    for (a, b) in ((4096 + 12288, 4096 + 12288 + 1024),):
+        sub = slice(a, b)
+        mask = orc.mask_from_slices([[0, b - a]], [[0, b - a]], [1], b - a, b - a)
+        ro, rl = orc.attn_fwd(q[sub].cpu(), k[sub].cpu(), v[sub].cpu(), mask, high_precision=True)
+        lo, ll = orc.attn_fwd(q[sub].cpu(), k[sub].cpu(), v[sub].cpu(), mask, high_precision=False)
+        orc.check_close("out", o1[sub].cpu(), ro, lo, "out")
+        orc.check_close("lse", m1.lse[sub].cpu(), rl, ll, "lse")

@@ -1,0 +1,154 @@
+"""CPU tests of the host-side CP planner: for several masks and cp sizes, simulate every rank's staged
+attention with the oracle on the planner's local slices + transfer tables and compare with the global
+oracle result (forward and the dK/dV reduction path)."""
+import pytest
+import torch
+
+from magiattention_b200.meta.planner import _restrict, make_attn_meta, make_dispatch_meta, slice_area
+from mask_configs import mask_configs
+from oracle import ffa_oracle as orc
+
+
+def _slices(cfg):
+    return [(q[0], q[1], k[0], k[1], t) for q, k, t in zip(cfg["q_ranges"], cfg["k_ranges"], cfg["types"])]
+
+
+@pytest.mark.parametrize("t", [0, 1, 2, 3])
+def test_restrict_exact(t):
+    """Band decomposition reproduces the restricted mask exactly, for random sub-rectangles."""
+    g = torch.Generator().manual_seed(t)
+    for _ in range(60):
+        q0 = int(torch.randint(0, 20, (1,), generator=g)); sq = int(torch.randint(1, 40, (1,), generator=g))
+        k0 = int(torch.randint(0, 20, (1,), generator=g)); sk = int(torch.randint(1, 40, (1,), generator=g))
+        s = (q0, q0 + sq, k0, k0 + sk, t)
+        a = int(torch.randint(0, 30, (1,), generator=g)); b = a + int(torch.randint(1, 40, (1,), generator=g))
+        c = int(torch.randint(0, 30, (1,), generator=g)); e = c + int(torch.randint(1, 40, (1,), generator=g))
+        N = 100
+        full = orc.mask_from_slices([[s[0], s[1]]], [[s[2], s[3]]], [t], N, N)
+        want = torch.zeros_like(full)
+        want[a:b, c:e] = full[a:b, c:e]
+        bands = _restrict(s, a, b, c, e)
+        got = torch.zeros_like(full)
+        for (x, y, kk0, kk1, tt) in bands:
+            m = orc.mask_from_slices([[x, y]], [[kk0, kk1]], [tt], N, N)
+            assert not (got & m).any(), "bands overlap"
+            got |= m
+        assert torch.equal(got, want), (s, a, b, c, e, bands)
+        assert sum(slice_area(bd) for bd in bands) == int(want.sum()) == slice_area(s, a, b, c, e)
+
+
+def _simulate(cfg_slices, T, cp, chunk, degree, H=2, HK=1, D=16, seed=0):
+    torch.manual_seed(seed)
+    q = torch.randn(T, H, D, dtype=torch.float64)
+    k = torch.randn(T, HK, D, dtype=torch.float64)
+    v = torch.randn(T, HK, D, dtype=torch.float64)
+    do = torch.randn(T, H, D, dtype=torch.float64)
+    mask = orc.mask_from_slices([[s[0], s[1]] for s in cfg_slices], [[s[2], s[3]] for s in cfg_slices],
+                                [s[4] for s in cfg_slices], T, T)
+    ref_o, ref_l = orc.attn_fwd(q, k, v, mask)
+    ref_dq, ref_dk, ref_dv = orc.attn_bwd(do, q, k, v, ref_o, ref_l, mask)
+    dm = make_dispatch_meta(cfg_slices, T, chunk, cp)
+    assert sorted(c for p in dm.partitions for c in p) == list(range(T // chunk))
+    comm, calc = make_attn_meta(cfg_slices, dm, degree)
+    pos = [dm.position_ids(r) for r in range(cp)]
+    ql, kl, vl, dol = ([x[p] for p in pos] for x in (q, k, v, do))
+    total_area = sum(cm.local_attn_arg.total_area + sum(a.total_area for a in cm.remote_attn_args_list) for cm in calc)
+    assert total_area == int(mask.sum()), "planner slices must tile the mask exactly"
+    dk_acc = [torch.zeros_like(x) for x in kl]
+    dv_acc = [torch.zeros_like(x) for x in vl]
+    outs, lses, dqs = [], [], []
+    # stage buffers through the naive world-level group_cast
+    stage_k, stage_v = [], []
+    for st in range(degree):
+        args = [comm[r].kv_group_collective_args_list[st] for r in range(cp)]
+        kw = dict(input_split_sizes=[a.input_split_size_list for a in args],
+                  dst_indices=[a.dst_indices_list for a in args], src_index=[a.src_index_list for a in args],
+                  output_split_sizes=[a.output_split_size_list for a in args])
+        for a in args:
+            assert sum(a.input_split_size_list) == dm.shard_seqlen
+        stage_k.append(orc.group_cast_ref(kl, **kw))
+        stage_v.append(orc.group_cast_ref(vl, **kw))
+    for r in range(cp):
+        cm = calc[r]
+        S = dm.shard_seqlen
+
+        def part(arg, kk, vv):
+            m = orc.mask_from_slices(arg.q_ranges, arg.k_ranges, arg.attn_type_map, S, kk.shape[0])
+            return m, orc.attn_fwd(ql[r], kk, vv, m)
+
+        m0, (o, l) = part(cm.local_attn_arg, kl[r], vl[r])
+        masks = [m0]
+        for st in range(degree):
+            m, (o2, l2) = part(cm.remote_attn_args_list[st], stage_k[st][r], stage_v[st][r])
+            masks.append(m)
+            o, l = orc.merge_out_lse(o, l, o2, l2)
+        torch.testing.assert_close(o, ref_o[pos[r]], atol=1e-10, rtol=1e-10)
+        fin = ~torch.isinf(ref_l[pos[r]])
+        assert torch.equal(torch.isinf(l), ~fin)
+        torch.testing.assert_close(l[fin], ref_l[pos[r]][fin], atol=1e-10, rtol=1e-10)
+        outs.append(o); lses.append(l)
+        # backward with global (o, l): local part + per-stage partials
+        dq, dk0, dv0 = orc.attn_bwd(dol[r], ql[r], kl[r], vl[r], o, l, masks[0])
+        dk_acc[r] += dk0; dv_acc[r] += dv0
+        parts_k, parts_v = [], []
+        for st in range(degree):
+            dq2, dkp, dvp = orc.attn_bwd(dol[r], ql[r], stage_k[st][r], stage_v[st][r], o, l, masks[1 + st])
+            dq = dq + dq2
+            parts_k.append(dkp); parts_v.append(dvp)
+        dqs.append((dq, parts_k, parts_v))
+        torch.testing.assert_close(dq, ref_dq[pos[r]], atol=1e-9, rtol=1e-9)
+    for st in range(degree):
+        args = [comm[r].kv_group_collective_args_list[st].to_group_reduce_args() for r in range(cp)]
+        kw = dict(input_split_sizes=[a["input_split_sizes"] for a in args], dst_index=[a["dst_index"] for a in args],
+                  src_indices=[a["src_indices"] for a in args], output_split_sizes=[a["output_split_sizes"] for a in args])
+        dk_acc = orc.group_reduce_ref([dqs[r][1][st] for r in range(cp)], dk_acc, **kw)
+        dv_acc = orc.group_reduce_ref([dqs[r][2][st] for r in range(cp)], dv_acc, **kw)
+    for r in range(cp):
+        torch.testing.assert_close(dk_acc[r], ref_dk[pos[r]], atol=1e-9, rtol=1e-9)
+        torch.testing.assert_close(dv_acc[r], ref_dv[pos[r]], atol=1e-9, rtol=1e-9)
+    return dm, comm, calc
+
+
+@pytest.mark.parametrize("name", ["causal", "full", "varlen_causal_1k", "sliding_window_causal", "all_types_aspects",
+                                  "sparse_attn_2k", "uncovered_rows", "varlen_block_causal_2k"])
+@pytest.mark.parametrize("cp,degree", [(2, 1), (4, 2), (8, 3)])
+def test_planner_matches_global_oracle(name, cp, degree):
+    cfg = next(c for c in mask_configs(4) if c["name"] == name)
+    T = cfg["seqlen"]
+    chunk = 16
+    pad = (-T) % (chunk * cp)
+    _simulate(_slices(cfg), T + pad, cp, chunk, degree)
+
+
+def test_causal_dispatch_is_balanced_and_zero_redundant():
+    """C4-like shape scaled down: causal, cp=8: equal area per rank, and every rank fetches only keys it can see
+    (reference planner finding, SURVEY App. A: per-rank area = 1.0000 x mean, remote rows < S)."""
+    T, cp, chunk = 4096, 8, 32
+    s = [(0, T, 0, T, 1)]
+    dm = make_dispatch_meta(s, T, chunk, cp)
+    comm, calc = make_attn_meta(s, dm, 2)
+    areas = [cm.local_attn_arg.total_area + sum(a.total_area for a in cm.remote_attn_args_list) for cm in calc]
+    assert max(areas) - min(areas) <= 0.002 * (sum(areas) / cp)
+    assert sum(areas) == T * (T + 1) // 2
+    for r in range(cp):
+        rows = sum(comm[r].num_remote_kv_tokens_per_stage)
+        assert rows <= T - dm.shard_seqlen
+        # remote slices of a causal mask are FULL except where a remote chunk holds the diagonal (never: own chunk)
+        for a in calc[r].remote_attn_args_list:
+            assert all(t == 0 for t in a.attn_type_map)
+
+
+def test_sliding_window_inference_known_answer():
+    """SURVEY App. A.2 known answer: cu_seqlens [0,3000,3500,8192], window (1024,0) -> area 6 959 950."""
+    from magiattention_b200.api import infer_attn_mask_from_cu_seqlens
+
+    qr, kr, ty, tq, tk = infer_attn_mask_from_cu_seqlens([0, 3000, 3500, 8192], [0, 3000, 3500, 8192], False, (1024, 0))
+    assert tq == tk == 8192
+    ints = [t.to_int_type() for t in ty]
+    assert orc.mask_area(qr.to_naive_ranges(), kr.to_naive_ranges(), ints) == 6959950
+    # brute-force band mask
+    m = orc.mask_from_slices(qr.to_naive_ranges(), kr.to_naive_ranges(), ints, 8192, 8192)
+    i = torch.arange(8192).unsqueeze(1); j = torch.arange(8192).unsqueeze(0)
+    doc = torch.bucketize(torch.arange(8192), torch.tensor([3000, 3500, 8192]), right=True)
+    want = (doc.unsqueeze(1) == doc.unsqueeze(0)) & (j <= i) & (j >= i - 1024)
+    assert torch.equal(m, want)
