@@ -251,7 +251,7 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     using OutT = typename std::conditional<kOutF32, float, typename std::conditional<kBF16, __nv_bfloat16, __half>::type>::type;
     OutT* orow = reinterpret_cast<OutT*>(args.out) + int64_t(row) * args.o_stride_t + int64_t(hq) * args.o_stride_h;
-    const bool skip_store = !row_ok || (args.accumulate && dead);  // accumulate + nothing new: keep old
+    const bool skip_store = !row_ok || (args.accumulate && dead && need_old);  // nothing new: keep the old partial
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       float o[32];

@@ -21,8 +21,9 @@ def _gather_global(x_local: torch.Tensor, meta: DispatchMeta, group) -> torch.Te
     if meta.cp_size == 1:
         gathered = x_local.unsqueeze(0)
     else:
-        gathered = x_local.new_empty((meta.cp_size, *x_local.shape))
-        dist.all_gather_into_tensor(gathered, x_local.contiguous(), group=group)
+        flat = x_local.new_empty((meta.cp_size * x_local.shape[0], *x_local.shape[1:]))
+        dist.all_gather_into_tensor(flat, x_local.contiguous(), group=group)
+        gathered = flat.reshape(meta.cp_size, *x_local.shape)
     out = x_local.new_empty((meta.num_chunks, cs, *x_local.shape[1:]))
     for r, part in enumerate(meta.partitions):
         idx = torch.as_tensor(part, device=x_local.device)

@@ -1,0 +1,124 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/b200_ffa.h declares; parameter blocks in the ctypes binding match the header field-for-field; host-only
+entry points (version, workspace sizing, argument validation that precedes any CUDA call) behave."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "b200_ffa.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from magiattention_b200.build import build
+    from magiattention_b200 import _lib
+
+    build()
+    return _lib.lib()
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    return re.findall(r"B200_API\s+[\w\s\*]+?\b(b200_\w+)\s*\(", src)
+
+
+def test_header_symbols_exported(lib):
+    names = _declared_functions()
+    assert len(names) >= 9
+    from magiattention_b200 import _lib
+
+    assert sorted(names) == sorted(_lib.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/b200_ffa.h but not exported"
+
+
+def _struct_fields(name):
+    src = open(HEADER).read()
+    end = src.index("} " + name + ";")
+    body = src[src.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        typ, rest = re.match(r"((?:const\s+)?\w+\s*\**)\s*(.*)", decl).groups()
+        for nm in rest.split(","):
+            fields.append((nm.strip().lstrip("*"), typ.replace(" ", "")))
+    return fields
+
+
+@pytest.mark.parametrize("cname,pyname", [("b200_ffa_fwd_params", "FwdParams"), ("b200_ffa_bwd_params", "BwdParams")])
+def test_ctypes_struct_matches_header(cname, pyname):
+    from magiattention_b200 import _lib
+
+    hdr = _struct_fields(cname)
+    py = getattr(_lib, pyname)._fields_
+    assert [n for n, _ in hdr] == [n for n, _ in py]
+    for (n, ht), (_, ct) in zip(hdr, py):
+        if "*" in ht:
+            assert ct is C.c_void_p, n
+        elif ht == "int32_t":
+            assert ct is C.c_int32, n
+        elif ht == "int64_t":
+            assert ct is C.c_int64, n
+        elif ht == "float":
+            assert ct is C.c_float, n
+        elif ht == "size_t":
+            assert ct is C.c_size_t, n
+        else:
+            raise AssertionError(f"unhandled header type {ht} for {n}")
+
+
+def test_version_and_workspace_sizing(lib):
+    from magiattention_b200 import _lib
+
+    assert lib.b200_ffa_version().decode() == "b200_ffa 0.1.0 sm_100a"
+    p = _lib.FwdParams()
+    p.total_q, p.num_slices = 262144, 1
+    w1 = lib.b200_ffa_fwd_workspace_bytes(C.byref(p))
+    p.num_slices = 64
+    w2 = lib.b200_ffa_fwd_workspace_bytes(C.byref(p))
+    assert 0 < w1 < w2 and w1 % 256 == 0 and w2 % 256 == 0
+    b = _lib.BwdParams()
+    b.total_q = b.total_k = 4096
+    b.num_heads_q, b.num_slices = 8, 3
+    assert lib.b200_ffa_bwd_workspace_bytes(C.byref(b)) >= 2 * 8 * (4096 + 128) * 4
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    """Bad arguments are rejected with a code + message before any CUDA work (never throws, never aborts)."""
+    from magiattention_b200 import _lib
+
+    p = _lib.FwdParams()
+    p.dtype, p.head_dim, p.num_heads_q, p.num_heads_kv = _lib.B200_BF16, 64, 2, 2
+    assert lib.b200_ffa_fwd(C.byref(p), None) == -4  # B200_ERR_UNSUPPORTED
+    assert b"head_dim" in lib.b200_ffa_last_error()
+    p.head_dim, p.num_heads_kv = 128, 3
+    assert lib.b200_ffa_fwd(C.byref(p), None) == -1
+    p.num_heads_kv, p.softcap = 2, 1.0
+    assert lib.b200_ffa_fwd(C.byref(p), None) == -4
+    assert lib.b200_ffa_fwd(None, None) == -1
+
+
+def test_product_path_has_no_host_fallback():
+    """The op refuses host tensors instead of silently computing on the CPU."""
+    import torch
+    from magiattention_b200.functional import flex_flash_attn_func
+
+    q = torch.randn(64, 2, 128, dtype=torch.bfloat16)
+    r = torch.tensor([[0, 64]], dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        flex_flash_attn_func(q, q, q, r, r, None)
+
+
+def test_no_oracle_import_in_product():
+    pkg = os.path.join(ROOT, "magiattention_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(d, f)).read()
+                assert "oracle" not in src, f"{f} references the oracle"

@@ -38,19 +38,19 @@ def _run_case(qr, kr, ty, T, TK, HQ, HK, dtype, seed=0, check_bwd=True):
     ty_t = torch.tensor(ty, dtype=torch.int32, device=dev)
     out, meta = flex_flash_attn_func(q, k, v, qr_t, kr_t, ty_t)
     mask = orc.mask_from_slices(qr, kr, ty, T, TK)
-    qc, kc, vc, doc = (x.detach().cpu() for x in (q, k, v, do))
+    qc, kc, vc, doc = (x.detach() for x in (q, k, v, do))  # oracle math runs on the GPU tensors (same code, fp64)
     ro, rl = orc.attn_fwd(qc, kc, vc, mask, high_precision=True)
     lo, ll = orc.attn_fwd(qc, kc, vc, mask, high_precision=False)
     ro64, _ = orc.attn_fwd(qc.double(), kc.double(), vc.double(), mask, high_precision=True)
-    orc.check_close("out", out.detach().cpu(), ro64, lo, "out")
-    orc.check_close("lse", meta.lse.cpu(), rl, ll, "lse")
+    orc.check_close("out", out.detach(), ro64, lo, "out")
+    orc.check_close("lse", meta.lse, rl, ll, "lse")
     if not check_bwd:
         return
     out.backward(do)
     ref = orc.attn_bwd(doc, qc.double(), kc.double(), vc.double(), ro64, rl.double(), mask, high_precision=True)
     lp = orc.attn_bwd(doc, qc, kc, vc, lo, ll, mask, high_precision=False)
     for name, g, r, l in zip(("dq", "dk", "dv"), (q.grad, k.grad, v.grad), ref, lp):
-        orc.check_close(name, g.cpu(), r, l, name)
+        orc.check_close(name, g, r, l, name)
 
 
 @pytest.mark.parametrize("cfg", mask_configs(1), ids=[c["name"] for c in mask_configs(1)])
@@ -102,7 +102,7 @@ def test_forward_accumulate_matches_lse_merge():
     scale = D ** -0.5
     o1, m1 = _flex_flash_attn_forward(q, k, v, None, "sh", None, None, qr1, kr1, ty1, scale, 0.0, torch.float32)
     o2, m2 = _flex_flash_attn_forward(q, k, v, None, "sh", None, None, qr2, kr2, ty2, scale, 0.0, torch.float32)
-    ref_o, ref_l = orc.merge_out_lse(o1.cpu(), m1.lse.cpu(), o2.cpu(), m2.lse.cpu())
+    ref_o, ref_l = (x.cpu() for x in orc.merge_out_lse(o1, m1.lse, o2, m2.lse))
     oa, la = o1.clone(), m1.lse.clone()
     _flex_flash_attn_forward(q, k, v, None, "sh", oa, la, qr2, kr2, ty2, scale, 0.0, torch.float32)
     torch.testing.assert_close(oa.cpu(), ref_o, atol=1e-5, rtol=1e-4)
@@ -110,7 +110,7 @@ def test_forward_accumulate_matches_lse_merge():
     # random accumulators, as the reference test does
     o_acc = torch.randn(T, H, D, dtype=torch.float32, device=dev)
     l_acc = torch.randn(T, H, dtype=torch.float32, device=dev)
-    ref_o, ref_l = orc.merge_out_lse(o_acc.cpu(), l_acc.cpu(), o2.cpu(), m2.lse.cpu())
+    ref_o, ref_l = (x.cpu() for x in orc.merge_out_lse(o_acc, l_acc, o2, m2.lse))
     _flex_flash_attn_forward(q, k, v, None, "sh", o_acc, l_acc, qr2, kr2, ty2, scale, 0.0, torch.float32)
     torch.testing.assert_close(o_acc.cpu(), ref_o, atol=1e-5, rtol=1e-4)
     torch.testing.assert_close(l_acc.cpu(), ref_l, atol=1e-5, rtol=1e-4)
@@ -118,7 +118,7 @@ def test_forward_accumulate_matches_lse_merge():
     from magiattention_b200 import _lib
     ob, lb = o1.clone(), m1.lse.clone()
     _lib.lse_merge(ob, lb, o2, m2.lse)
-    ref_o, ref_l = orc.merge_out_lse(o1.cpu(), m1.lse.cpu(), o2.cpu(), m2.lse.cpu())
+    ref_o, ref_l = (x.cpu() for x in orc.merge_out_lse(o1, m1.lse, o2, m2.lse))
     torch.testing.assert_close(ob.cpu(), ref_o, atol=1e-5, rtol=1e-4)
     torch.testing.assert_close(lb.cpu(), ref_l, atol=1e-5, rtol=1e-4)
 
@@ -202,7 +202,7 @@ def test_full_size_properties_c2_like():
     for (a, b) in ((4096 + 12288, 4096 + 12288 + 1024),):
         sub = slice(a, b)
         mask = orc.mask_from_slices([[0, b - a]], [[0, b - a]], [1], b - a, b - a)
-        ro, rl = orc.attn_fwd(q[sub].cpu(), k[sub].cpu(), v[sub].cpu(), mask, high_precision=True)
-        lo, ll = orc.attn_fwd(q[sub].cpu(), k[sub].cpu(), v[sub].cpu(), mask, high_precision=False)
-        orc.check_close("out", o1[sub].cpu(), ro, lo, "out")
-        orc.check_close("lse", m1.lse[sub].cpu(), rl, ll, "lse")
+        ro, rl = orc.attn_fwd(q[sub], k[sub], v[sub], mask, high_precision=True)
+        lo, ll = orc.attn_fwd(q[sub], k[sub], v[sub], mask, high_precision=False)
+        orc.check_close("out", o1[sub], ro, lo, "out")
+        orc.check_close("lse", m1.lse[sub], rl, ll, "lse")

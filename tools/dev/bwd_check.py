@@ -49,7 +49,7 @@ def run_case(name, T, TK, HQ, HK, qr, kr, ty, dtype, dkv_f32=False, seed=0):
     ok = True
     msgs = []
     for nm, got, r, l in zip(("dq", "dk", "dv"), (dq, dk, dv), ref, lp):
-        g = got.cpu().double()
+        g = got.double()
         err = (g - r.double()).abs().max().item()
         err_lp = (l.double() - r.double()).abs().max().item()
         nan = bool(torch.isnan(g).any())
