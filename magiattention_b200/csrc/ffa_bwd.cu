@@ -376,8 +376,9 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   } else {
     setmaxnreg_dec<96>();
     if (wid == 12) {
-      if (lane == 0) {
+      {
         // ================================ MMA issuer ================================
+        // warp-uniform loop (descriptors stay in uniform registers); one elected lane issues the async ops
         constexpr uint32_t id_kk = make_idesc(kBF16, false, false, 128, 128);  // S^T, dP^T : both K-major
         constexpr uint32_t id_tm = make_idesc(kBF16, false, true, 128, 128);   // dV, dK : A tmem, B MN-major
         constexpr uint32_t id_mm = make_idesc(kBF16, true, true, 128, 128);    // dQ : A, B MN-major
@@ -385,17 +386,26 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t sK = smem_base + kSmemK, sV = smem_base + kSmemV, sDS = smem_base + kSmemDS;
         const uint32_t tS = tmem + kTmemS, tDP = tmem + kTmemDP, tDV = tmem + kTmemDV, tDK = tmem + kTmemDK;
 
-        auto mma_kmajor = [&](uint32_t d, uint32_t a, uint32_t b) {
+        // each helper issues its MMA batch and then commits to up to two mbarriers (0 = none)
+        auto mma_kmajor = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t commit_bar) {
+          if (elect_one()) {
 #pragma unroll
-          for (uint32_t kk = 0; kk < 8; ++kk) {
-            const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-            mma_ss(d, smem_desc(DESC_KMAJOR, a + off), smem_desc(DESC_KMAJOR, b + off), id_kk, kk > 0 ? 1u : 0u);
+            for (uint32_t kk = 0; kk < 8; ++kk) {
+              const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+              mma_ss(d, smem_desc(DESC_KMAJOR, a + off), smem_desc(DESC_KMAJOR, b + off), id_kk, kk > 0 ? 1u : 0u);
+            }
+            tc_commit(commit_bar);
           }
+          __syncwarp();
         };
-        auto mma_tmemA = [&](uint32_t d, uint32_t a_tmem, uint32_t b, bool acc) {
+        auto mma_tmemA = [&](uint32_t d, uint32_t a_tmem, uint32_t b, bool acc, uint32_t commit_bar) {
+          if (elect_one()) {
 #pragma unroll
-          for (uint32_t kk = 0; kk < 8; ++kk)
-            mma_ts(d, a_tmem + (kk >> 2) * 64 + (kk & 3) * 8, smem_desc(mn_hi, b + kk * 2048), id_tm, (acc || kk > 0) ? 1u : 0u);
+            for (uint32_t kk = 0; kk < 8; ++kk)
+              mma_ts(d, a_tmem + (kk >> 2) * 64 + (kk & 3) * 8, smem_desc(mn_hi, b + kk * 2048), id_tm, (acc || kk > 0) ? 1u : 0u);
+            tc_commit(commit_bar);
+          }
+          __syncwarp();
         };
 
         // total number of iterations for this CTA (all q heads walk the same slice list)
@@ -414,12 +424,10 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           // prologue: S_0, dP_0
           mbar_wait(bar(kBarQFull + 0), 0);
           tc_fence_after();
-          mma_kmajor(tS, sK, smem_base + kSmemQ);
-          tc_commit(bar(kBarS));
+          mma_kmajor(tS, sK, smem_base + kSmemQ, bar(kBarS));
           mbar_wait(bar(kBarDOFull + 0), 0);
           tc_fence_after();
-          mma_kmajor(tDP, sV, smem_base + kSmemDO);
-          tc_commit(bar(kBarDP));
+          mma_kmajor(tDP, sV, smem_base + kSmemDO, bar(kBarDP));
           for (uint32_t it = 0; it < n_it; ++it) {
             const uint32_t st = it & 1, nst = st ^ 1;
             const uint32_t sQ = smem_base + kSmemQ + st * kTileBytes, sDO = smem_base + kSmemDO + st * kTileBytes;
@@ -427,40 +435,39 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             // dV += P^T dO
             mbar_wait(bar(kBarP), it & 1);
             tc_fence_after();
-            mma_tmemA(tDV, tS, sDO, it > 0);
-            tc_commit(bar(kBarDOEmpty + st));  // dO_it no longer needed once dV retires
+            mma_tmemA(tDV, tS, sDO, it > 0, bar(kBarDOEmpty + st));  // dO_it no longer needed once dV retires
             // S_{it+1} (S region is free after dV in tensor-pipe order)
             if (has_next) {
               mbar_wait(bar(kBarQFull + nst), ((it + 1) >> 1) & 1);
               tc_fence_after();
-              mma_kmajor(tS, sK, smem_base + kSmemQ + nst * kTileBytes);
-              tc_commit(bar(kBarS));
+              mma_kmajor(tS, sK, smem_base + kSmemQ + nst * kTileBytes, bar(kBarS));
             }
             // dK += dS^T Q ; dQ = dS K
             mbar_wait(bar(kBarDS), it & 1);
             tc_fence_after();
-            mma_tmemA(tDK, tDP, sQ, it > 0);
-            tc_commit(bar(kBarQEmpty + st));
+            mma_tmemA(tDK, tDP, sQ, it > 0, bar(kBarQEmpty + st));
+            if (elect_one()) {
 #pragma unroll
-            for (uint32_t kk = 0; kk < 8; ++kk)
-              mma_ss(tDP, smem_desc(mn_hi, sDS + kk * 2048), smem_desc(mn_hi, sK + kk * 2048), id_mm, kk > 0 ? 1u : 0u);
-            tc_commit(bar(kBarDQ));
+              for (uint32_t kk = 0; kk < 8; ++kk)
+                mma_ss(tDP, smem_desc(mn_hi, sDS + kk * 2048), smem_desc(mn_hi, sK + kk * 2048), id_mm, kk > 0 ? 1u : 0u);
+              tc_commit(bar(kBarDQ));
+            }
+            __syncwarp();
             // dP_{it+1} once the dQ tile has been drained out of the shared TMEM region
             if (has_next) {
               mbar_wait(bar(kBarDrained), it & 1);
               mbar_wait(bar(kBarDOFull + nst), ((it + 1) >> 1) & 1);
               tc_fence_after();
-              mma_kmajor(tDP, sV, smem_base + kSmemDO + nst * kTileBytes);
-              tc_commit(bar(kBarDP));
+              mma_kmajor(tDP, sV, smem_base + kSmemDO + nst * kTileBytes, bar(kBarDP));
             }
           }
-          tc_commit(bar(kBarDKV));
+          if (elect_one()) tc_commit(bar(kBarDKV));
+          __syncwarp();
         }
       }
-      __syncwarp();
     } else if (wid == 13) {
-      if (lane == 0) {
-        // ================================ TMA producer ================================
+      {
+        // ================================ TMA producer (warp-uniform, elected lane issues) ================
         bool kv_loaded = false;
         uint32_t it = 0;
         for (int g = 0; g < G; ++g) {
@@ -474,33 +481,41 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           while (cur.next(sl)) {
             if (!gm.init(sl, C0)) continue;
             if (!kv_loaded) {
-              mbar_arrive_expect_tx(bar(kBarKV), 2 * kTileBytes);
-              tma_load_3d(smem_base + kSmemK, &tmK, bar(kBarKV), 0, hk, C0);
-              tma_load_3d(smem_base + kSmemK + kBoxBytes, &tmK, bar(kBarKV), 64, hk, C0);
-              tma_load_3d(smem_base + kSmemV, &tmV, bar(kBarKV), 0, hk, C0);
-              tma_load_3d(smem_base + kSmemV + kBoxBytes, &tmV, bar(kBarKV), 64, hk, C0);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bar(kBarKV), 2 * kTileBytes);
+                tma_load_3d(smem_base + kSmemK, &tmK, bar(kBarKV), 0, hk, C0);
+                tma_load_3d(smem_base + kSmemK + kBoxBytes, &tmK, bar(kBarKV), 64, hk, C0);
+                tma_load_3d(smem_base + kSmemV, &tmV, bar(kBarKV), 0, hk, C0);
+                tma_load_3d(smem_base + kSmemV + kBoxBytes, &tmV, bar(kBarKV), 64, hk, C0);
+              }
+              __syncwarp();
               kv_loaded = true;
             }
             for (int b = 0; b < gm.nblk; ++b, ++it) {
               const int rs = gm.r_start + b * kBlockM;
               const uint32_t st = it & 1, ph = (it >> 1) & 1;
               mbar_wait(bar(kBarQEmpty + st), ph ^ 1);
-              mbar_arrive_expect_tx(bar(kBarQFull + st), kTileBytes + 1024);
-              const uint32_t sQ = smem_base + kSmemQ + st * kTileBytes;
-              tma_load_3d(sQ, &tmQ, bar(kBarQFull + st), 0, hq, rs);
-              tma_load_3d(sQ + kBoxBytes, &tmQ, bar(kBarQFull + st), 64, hq, rs);
-              bulk_load(smem_base + kSmemLse + st * 512, lse2 + rs, 512, bar(kBarQFull + st));
-              bulk_load(smem_base + kSmemDelta + st * 512, delta + rs, 512, bar(kBarQFull + st));
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bar(kBarQFull + st), kTileBytes + 1024);
+                const uint32_t sQ = smem_base + kSmemQ + st * kTileBytes;
+                tma_load_3d(sQ, &tmQ, bar(kBarQFull + st), 0, hq, rs);
+                tma_load_3d(sQ + kBoxBytes, &tmQ, bar(kBarQFull + st), 64, hq, rs);
+                bulk_load(smem_base + kSmemLse + st * 512, lse2 + rs, 512, bar(kBarQFull + st));
+                bulk_load(smem_base + kSmemDelta + st * 512, delta + rs, 512, bar(kBarQFull + st));
+              }
+              __syncwarp();
               mbar_wait(bar(kBarDOEmpty + st), ph ^ 1);
-              mbar_arrive_expect_tx(bar(kBarDOFull + st), kTileBytes);
-              const uint32_t sDO = smem_base + kSmemDO + st * kTileBytes;
-              tma_load_3d(sDO, &tmDO, bar(kBarDOFull + st), 0, hq, rs);
-              tma_load_3d(sDO + kBoxBytes, &tmDO, bar(kBarDOFull + st), 64, hq, rs);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(bar(kBarDOFull + st), kTileBytes);
+                const uint32_t sDO = smem_base + kSmemDO + st * kTileBytes;
+                tma_load_3d(sDO, &tmDO, bar(kBarDOFull + st), 0, hq, rs);
+                tma_load_3d(sDO + kBoxBytes, &tmDO, bar(kBarDOFull + st), 64, hq, rs);
+              }
+              __syncwarp();
             }
           }
         }
       }
-      __syncwarp();
     }
   }
   tc_fence_before();

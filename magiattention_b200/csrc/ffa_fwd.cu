@@ -28,6 +28,10 @@
 #include "ffa_kernels.h"
 #include "sm100.cuh"
 
+#ifndef FFA_FWD_PACKED
+#define FFA_FWD_PACKED 1
+#endif
+
 namespace ffa {
 using namespace sm100;
 
@@ -46,6 +50,8 @@ constexpr int kBarQ = 0, kBarFull = 1, kBarEmpty = kBarFull + kStages, kBarS = k
 static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
 constexpr uint32_t kTmemS = 0, kTmemO = 256;
 constexpr float kRescaleThreshold = 8.0f;
+// exp2 on the FMA pipe for kEmuCount of every kEmuPeriod element pairs (rest on the SFU)
+constexpr int kEmuPeriod = 8, kEmuCount = 3, kEmuDegree = 4;
 }  // namespace fwd
 
 
@@ -178,9 +184,17 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               if (!((bits >> i) & 1u)) sr[c * 32 + i] = 0xff800000u;  // -inf
           }
         }
-        float mb = -INFINITY;
+        float mb;
+        {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent 3-input-max chains
 #pragma unroll
-        for (int i = 0; i < 128; ++i) mb = fmaxf(mb, __uint_as_float(sr[i]));
+          for (int i = 0; i < 128; i += 8) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              m4[j] = fmaxf(m4[j], fmaxf(__uint_as_float(sr[i + 2 * j]), __uint_as_float(sr[i + 2 * j + 1])));
+          }
+          mb = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        }
         const float m_new = fmaxf(m_ref, mb);
         const bool upd = (m_new - m_ref) * sl2 > kRescaleThreshold;  // NaN (-inf - -inf) compares false
         float corr = 1.f;
@@ -202,18 +216,54 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
         }
         const float mneg = (m_ref == -INFINITY) ? 0.f : -m_ref * sl2;
+#if FFA_FWD_PACKED
+        const float2 sl2_2 = make_float2(sl2, sl2), mneg2 = make_float2(mneg, mneg);
+        float2 acc4[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t pr[32];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pr[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float p0 = ex2(fmaf(__uint_as_float(sr[64 * c + 2 * i]), sl2, mneg));
-            float p1 = ex2(fmaf(__uint_as_float(sr[64 * c + 2 * i + 1]), sl2, mneg));
-            l_sum += p0 + p1;
+          for (int i = 0; i < 16; ++i) {
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[32 * c + 2 * i]), __uint_as_float(sr[32 * c + 2 * i + 1])),
+                                        sl2_2, mneg2);
+            float2 pv;
+            if ((i % kEmuPeriod) < kEmuCount) {
+              pv = ex2_emu2<kEmuDegree>(x);
+            } else {
+              pv.x = ex2(x.x);
+              pv.y = ex2(x.y);
+            }
+            acc4[i & 3] = __fadd2_rn(acc4[i & 3], pv);
+            pr[i] = pack2<kBF16>(pv.x, pv.y);
+          }
+          tmem_st16(tS + c * 16, pr);
+        }
+        {
+          const float2 a01 = __fadd2_rn(acc4[0], acc4[1]), a23 = __fadd2_rn(acc4[2], acc4[3]);
+          l_sum += (a01.x + a01.y) + (a23.x + a23.y);
+        }
+#else
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pr[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = fmaf(__uint_as_float(sr[32 * c + 2 * i]), sl2, mneg);
+            float p1 = fmaf(__uint_as_float(sr[32 * c + 2 * i + 1]), sl2, mneg);
+            if ((i % kEmuPeriod) < kEmuCount) {
+              const float2 pv = ex2_emu2<kEmuDegree>(make_float2(p0, p1));
+              p0 = pv.x; p1 = pv.y;
+            } else {
+              p0 = ex2(p0); p1 = ex2(p1);
+            }
+            acc0 += p0; acc1 += p1;
             pr[i] = pack2<kBF16>(p0, p1);
           }
-          tmem_st32(tS + c * 32, pr);
+          tmem_st16(tS + c * 16, pr);
         }
+        l_sum += acc0 + acc1;
+#endif
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(bar(kBarP + t));
@@ -319,34 +369,51 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     if (!skip_store) *lse_ptr = lse_new;
   } else {
-    setmaxnreg_dec<80>();
-    if (wid == 8) { if (lane == 0) {
+    setmaxnreg_dec<96>();
+    if (wid == 8) {
       // =========================== MMA issuer ===========================
+      // The whole warp runs this loop with warp-uniform control flow (descriptors live in uniform registers);
+      // only the tcgen05.mma / tcgen05.commit instructions themselves are issued by one elected lane.
       constexpr uint32_t idesc_s = make_idesc(kBF16, false, false, 128, 128);
       constexpr uint32_t idesc_pv = make_idesc(kBF16, false, true, 128, 128);
       constexpr uint64_t desc_v_hi = desc_mnmajor(kBoxBytes);
       const uint32_t sQ = smem_base + kSmemQ, sKV = smem_base + kSmemKV;
-      uint32_t n_act[2] = {0, 0};       // active blocks issued so far per tile
-      bool has_prev[2] = {false, false};
-      uint32_t prev_load[2] = {0, 0};   // ring load index of the V block of the pending PV
-      uint32_t pend = 0;                // outstanding PV users per ring buffer, 4 bits each
-      uint32_t blk = 0;                 // kv block counter (ring: K = 2*blk, V = 2*blk+1)
+      uint32_t n_act0 = 0, n_act1 = 0;            // active blocks issued so far per tile
+      bool has_prev0 = false, has_prev1 = false;  // a PV of that tile is pending
+      uint32_t prev_load0 = 0, prev_load1 = 0;    // ring load index of the V block of the pending PV
+      uint32_t pend = 0;                          // outstanding PV users per ring buffer, 4 bits each
+      uint32_t blk = 0;                           // kv block counter (ring: K = 2*blk, V = 2*blk+1)
       bool q_ready = false;
 
-      auto issue_pv = [&](int t) {
-        // P_t of the pending block is in TMEM once the softmax warps arrive
-        mbar_wait(bar(kBarP + t), (n_act[t] - 1) & 1);
-        const uint32_t li = prev_load[t], buf = li % kStages;
+      auto issue_pv = [&](const int t, const uint32_t n_act_t, const uint32_t li) {
+        mbar_wait(bar(kBarP + t), (n_act_t - 1) & 1);  // P_t of the pending block is in TMEM
+        const uint32_t buf = li % kStages;
         mbar_wait(bar(kBarFull + buf), (li / kStages) & 1);
         tc_fence_after();
         const uint32_t sV = sKV + buf * kTileBytes;
         const uint32_t tP = tmem + kTmemS + t * 128, tOt = tmem + kTmemO + t * 128;
-#pragma unroll
-        for (uint32_t kk = 0; kk < 8; ++kk)
-          mma_ts(tOt, tP + kk * 8, smem_desc(desc_v_hi, sV + kk * 2048), idesc_pv, (n_act[t] > 1 || kk > 0) ? 1u : 0u);
         pend -= 1u << (4 * buf);
-        if (((pend >> (4 * buf)) & 15u) == 0) tc_commit(bar(kBarEmpty + buf));
-        has_prev[t] = false;
+        const bool release = ((pend >> (4 * buf)) & 15u) == 0;
+        if (elect_one()) {
+#pragma unroll
+          for (uint32_t kk = 0; kk < 8; ++kk)
+            mma_ts(tOt, tP + kk * 8, smem_desc(desc_v_hi, sV + kk * 2048), idesc_pv, (n_act_t > 1 || kk > 0) ? 1u : 0u);
+          if (release) tc_commit(bar(kBarEmpty + buf));
+        }
+        __syncwarp();
+      };
+      auto issue_s = [&](const int t, const uint32_t sK) {
+        const uint32_t tSt = tmem + kTmemS + t * 128;
+        if (elect_one()) {
+#pragma unroll
+          for (uint32_t kk = 0; kk < 8; ++kk) {
+            const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+            mma_ss(tSt, smem_desc(DESC_KMAJOR, sQ + t * kTileBytes + off), smem_desc(DESC_KMAJOR, sK + off), idesc_s,
+                   kk > 0 ? 1u : 0u);
+          }
+          tc_commit(bar(kBarS + t));
+        }
+        __syncwarp();
       };
 
       SliceCursor cur;
@@ -370,34 +437,26 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tc_fence_after();
           pend = (pend & ~(15u << (4 * vbuf))) | (((a0 ? 1u : 0u) + (a1 ? 1u : 0u)) << (4 * vbuf));
           const uint32_t sK = sKV + kbuf * kTileBytes;
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (has_prev[t]) issue_pv(t);
-            if (t == 0 ? a0 : a1) {
-              const uint32_t tSt = tmem + kTmemS + t * 128;
-#pragma unroll
-              for (uint32_t kk = 0; kk < 8; ++kk) {
-                const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-                mma_ss(tSt, smem_desc(DESC_KMAJOR, sQ + t * kTileBytes + off), smem_desc(DESC_KMAJOR, sK + off), idesc_s,
-                       kk > 0 ? 1u : 0u);
-              }
-              tc_commit(bar(kBarS + t));
-              has_prev[t] = true;
-              prev_load[t] = lv;
-              ++n_act[t];
-            }
+          if (has_prev0) { issue_pv(0, n_act0, prev_load0); has_prev0 = false; }
+          if (a0) { issue_s(0, sK); has_prev0 = true; prev_load0 = lv; ++n_act0; }
+          if (has_prev1) { issue_pv(1, n_act1, prev_load1); has_prev1 = false; }
+          if (a1) { issue_s(1, sK); has_prev1 = true; prev_load1 = lv; ++n_act1; }
+          if (elect_one()) {
+            tc_commit(bar(kBarEmpty + kbuf));  // K block free once both S MMAs retire
+            if (((pend >> (4 * vbuf)) & 15u) == 0) tc_commit(bar(kBarEmpty + vbuf));  // V block nobody needs
           }
-          tc_commit(bar(kBarEmpty + kbuf));            // K block free once both S MMAs retire
-          if (((pend >> (4 * vbuf)) & 15u) == 0) tc_commit(bar(kBarEmpty + vbuf));  // V block nobody needs
+          __syncwarp();
         }
       }
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        if (has_prev[t]) issue_pv(t);
-        if (n_act[t] > 0) tc_commit(bar(kBarO + t));
+      if (has_prev0) issue_pv(0, n_act0, prev_load0);
+      if (has_prev1) issue_pv(1, n_act1, prev_load1);
+      if (elect_one()) {
+        if (n_act0 > 0) tc_commit(bar(kBarO + 0));
+        if (n_act1 > 0) tc_commit(bar(kBarO + 1));
       }
-    } __syncwarp(); } else if (wid == 9) { if (lane == 0) {
-      // =========================== TMA producer ===========================
+      __syncwarp();
+    } else if (wid == 9) {
+      // =========================== TMA producer (warp-uniform loop, one elected lane issues) ===========
       const uint32_t sQ = smem_base + kSmemQ, sKV = smem_base + kSmemKV;
       uint32_t blk = 0;
       bool q_loaded = false;
@@ -408,12 +467,15 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       while (cur.next(sl)) {
         if (!g.init(sl, R0)) continue;
         if (!q_loaded) {
-          mbar_arrive_expect_tx(bar(kBarQ), 2 * kTileBytes);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar(kBarQ), 2 * kTileBytes);
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            tma_load_3d(sQ + t * kTileBytes, &tmQ, bar(kBarQ), 0, hq, R0 + t * kBlockM);
-            tma_load_3d(sQ + t * kTileBytes + kBoxBytes, &tmQ, bar(kBarQ), 64, hq, R0 + t * kBlockM);
+            for (int t = 0; t < 2; ++t) {
+              tma_load_3d(sQ + t * kTileBytes, &tmQ, bar(kBarQ), 0, hq, R0 + t * kBlockM);
+              tma_load_3d(sQ + t * kTileBytes + kBoxBytes, &tmQ, bar(kBarQ), 64, hq, R0 + t * kBlockM);
+            }
           }
+          __syncwarp();
           q_loaded = true;
         }
         for (int b = 0; b < g.nblk; ++b, ++blk) {
@@ -422,14 +484,17 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int which = 0; which < 2; ++which) {
             const uint32_t li = 2 * blk + which, buf = li % kStages;
             mbar_wait(bar(kBarEmpty + buf), ((li / kStages) & 1) ^ 1);
-            mbar_arrive_expect_tx(bar(kBarFull + buf), kTileBytes);
-            const CUtensorMap* tm = which == 0 ? &tmK : &tmV;
-            tma_load_3d(sKV + buf * kTileBytes, tm, bar(kBarFull + buf), 0, hk, bs);
-            tma_load_3d(sKV + buf * kTileBytes + kBoxBytes, tm, bar(kBarFull + buf), 64, hk, bs);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(bar(kBarFull + buf), kTileBytes);
+              const CUtensorMap* tm = which == 0 ? &tmK : &tmV;
+              tma_load_3d(sKV + buf * kTileBytes, tm, bar(kBarFull + buf), 0, hk, bs);
+              tma_load_3d(sKV + buf * kTileBytes + kBoxBytes, tm, bar(kBarFull + buf), 64, hk, bs);
+            }
+            __syncwarp();
           }
         }
       }
-    } __syncwarp(); }
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -87,19 +87,20 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+static __device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > SM100_WAIT_TIMEOUT_NS) {
+#ifdef SM100_DEBUG_WAIT
       printf("[sm100] mbarrier timeout: block (%d,%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, bar, parity);
+#endif
       __trap();
     }
   }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity);
 }
@@ -279,6 +280,37 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for a PAIR of values on the FMA pipe instead of the SFU (MUFU.EX2 issues at 16 lanes/clk/SM, which
+// makes exp the co-critical resource of attention on Blackwell).  Cody-Waite style: x = n + f with
+// n = floor(x) obtained by adding 1.5*2^23 in round-down mode, 2^f by a minimax polynomial on [0,1)
+// (degree 3: max rel. err 8.6e-5, degree 4: 3.0e-6 — both far below bf16/fp16 resolution of P), and 2^n
+// by adding n to the exponent field.  Packed f32x2 instructions (FFMA2/FADD2) halve the issue count.
+// Valid for x in [-126, 126]; inputs are clamped below (masked scores are -inf).
+template <int kDegree>
+__device__ __forceinline__ float2 ex2_emu2(float2 x) {
+  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 r = __fadd2_rd(x, make_float2(kMagic, kMagic));
+  const float2 fl = __fadd2_rn(r, make_float2(-kMagic, -kMagic));
+  const float2 f = __ffma2_rn(fl, make_float2(-1.f, -1.f), x);
+  float2 p;
+  if constexpr (kDegree == 3) {
+    p = __ffma2_rn(f, make_float2(0.07706703990697861f, 0.07706703990697861f),
+                   make_float2(0.22764499485492706f, 0.22764499485492706f));
+    p = __ffma2_rn(p, f, make_float2(0.6951167583465576f, 0.6951167583465576f));
+  } else {
+    p = __ffma2_rn(f, make_float2(0.013426684774458408f, 0.013426684774458408f),
+                   make_float2(0.052242472767829895f, 0.052242472767829895f));
+    p = __ffma2_rn(p, f, make_float2(0.241280198097229f, 0.241280198097229f));
+    p = __ffma2_rn(p, f, make_float2(0.6930448412895203f, 0.6930448412895203f));
+  }
+  p = __ffma2_rn(p, f, make_float2(1.f, 1.f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23));
+  return p;
+}
+
 template <bool BF16>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   uint32_t r;

@@ -308,6 +308,18 @@ RTOL = {"out": 0.05, "lse": 1e-3, "dq": 0.3, "dk": 0.15, "dv": 0.05}
 ATOL = 1e-8
 
 
+def grad_atol(ref: torch.Tensor) -> float:
+    """Epsilon of the gradient mismatch-ratio test: the reference's EPSILON (1e-8, "to avoid division by zero",
+    testing/precision.py:33) made scale-relative, 1e-8 + 2e-5 * ||ref||_inf.  Reason: a row with exactly ONE visible
+    key (first row of every square causal slice, every row of a square bi-causal slice) has P = 1, hence
+    dS = P*(dP - delta) = 0 exactly in exact arithmetic; the kernel's delta = rowsum(O*dO) and dP = dO.V^T are both
+    fp32 sums of the same products in different orders, so dS ~ 1e-7*|dP| instead of 0 and every element of such a
+    dq row would count as a "mismatch" against an expected 0 under an absolute 1e-8.  The reference sidesteps the
+    issue by skipping every case containing bi-causal slices (tests/test_attn/test_flex_flash_attn.py:1150-1154);
+    its torch autograd low-precision oracle rounds delta and dP to the same bf16 value and so returns exact 0."""
+    return ATOL + 2e-5 * float(ref.abs().max())
+
+
 def _mismatch_ratio(a: torch.Tensor, ref: torch.Tensor, atol: float, rtol: float) -> float:
     a, ref = a.double(), ref.double()
     both_inf = torch.isinf(a) & torch.isinf(ref) & (a == ref)
@@ -323,18 +335,25 @@ def _inf_norm(x: torch.Tensor) -> float:
     return float(x.abs().max()) if x.numel() else 0.0
 
 
-def check_close(name: str, test: torch.Tensor, ref_hp: torch.Tensor, ref_lp: torch.Tensor, kind: str) -> dict:
+def check_close(name: str, test: torch.Tensor, ref_hp: torch.Tensor, ref_lp: torch.Tensor, kind: str,
+                atol: float = ATOL) -> dict:
     """The reference's two-sided rule: ||test-ref64||inf <= 2*||ref_lp-ref64||inf AND
     mismatch(test) <= max(2*mismatch(ref_lp), small floor) capped at 0.75.
-    Returns a report dict; raises AssertionError on violation."""
+    Returns a report dict; raises AssertionError on violation.
+
+    ``atol`` is the reference's 1e-8 except where a test says otherwise: masks with SQUARE bi-causal slices have
+    rows with exactly one visible key, whose true dS (hence dq/dk) is exactly 0 — any fp32 summation-order
+    difference between delta = rowsum(O*dO) and dP then counts as a "mismatch" against an expected 0.  The
+    reference skips every such case outright (tests/test_attn/test_flex_flash_attn.py:1150-1154,
+    tests/test_pipeline.py:1049-1056); we keep the case and pass a scale-relative atol instead."""
     t, hp, lp = test.double(), ref_hp.double(), ref_lp.double()
     assert torch.equal(torch.isinf(t), torch.isinf(hp)), f"{name}: -inf pattern differs from oracle"
     assert not torch.isnan(t).any(), f"{name}: NaN in result"
     norm_t = _inf_norm(torch.where(torch.isinf(hp), torch.zeros_like(t), t - hp))
     norm_lp = _inf_norm(torch.where(torch.isinf(hp), torch.zeros_like(lp), lp - hp))
     rtol = RTOL[kind]
-    mm_t = _mismatch_ratio(t, hp, ATOL, rtol)
-    mm_lp = _mismatch_ratio(lp, hp, ATOL, rtol)
+    mm_t = _mismatch_ratio(t, hp, atol, rtol)
+    mm_lp = _mismatch_ratio(lp, hp, atol, rtol)
     thres = min(max(MISMATCH_THRES_RATIO * mm_lp, 1e-4), MAX_MISMATCH_THRES)
     rep = dict(name=name, norm=norm_t, norm_ref=norm_lp, mismatch=mm_t, mismatch_ref=mm_lp, thres=thres)
     norm_floor = 1e-6 if kind == "lse" else 0.0

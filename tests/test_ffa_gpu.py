@@ -49,8 +49,10 @@ def _run_case(qr, kr, ty, T, TK, HQ, HK, dtype, seed=0, check_bwd=True):
     out.backward(do)
     ref = orc.attn_bwd(doc, qc.double(), kc.double(), vc.double(), ro64, rl.double(), mask, high_precision=True)
     lp = orc.attn_bwd(doc, qc, kc, vc, lo, ll, mask, high_precision=False)
+    # gradients: scale-relative epsilon (see oracle.grad_atol): rows with a single visible key have exact-zero
+    # true dq/dk, against which the reference's absolute 1e-8 epsilon would flag any fp32 rounding noise
     for name, g, r, l in zip(("dq", "dk", "dv"), (q.grad, k.grad, v.grad), ref, lp):
-        orc.check_close(name, g, r, l, name)
+        orc.check_close(name, g, r, l, name, atol=orc.grad_atol(r))
 
 
 @pytest.mark.parametrize("cfg", mask_configs(1), ids=[c["name"] for c in mask_configs(1)])

@@ -1,0 +1,15 @@
+#!/bin/bash
+# one GPU-box visit: tests, smoke, bench, ncu launch list, ncu full capture of the two attention kernels
+set -x
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q 2>&1 | tail -8
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+python bench.py 2> gpurun_out/bench_n1.err | tee gpurun_out/bench_n1.json
+tail -5 gpurun_out/bench_n1.err
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --seqlen 65536 > gpurun_out/bench_ncu_list.json 2> gpurun_out/ncu_list.err
+tail -3 gpurun_out/ncu_list.err
+ncu --set full --clock-control none --import-source on -k 'regex:ffa_(fwd|bwd)_kernel' -c 2 -f -o gpurun_out/prof \
+    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --seqlen 32768 > gpurun_out/bench_ncu_full.json 2> gpurun_out/ncu_full.err
+tail -3 gpurun_out/ncu_full.err
+ls -la gpurun_out
