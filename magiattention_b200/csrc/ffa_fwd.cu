@@ -369,7 +369,8 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     if (!skip_store) *lse_ptr = lse_new;
   } else {
-    setmaxnreg_dec<96>();
+    // register pool = 384 threads x 168 regs (launch bounds) = 64512 = 256 x 208 + 128 x 88
+    setmaxnreg_dec<88>();
     if (wid == 8) {
       // =========================== MMA issuer ===========================
       // The whole warp runs this loop with warp-uniform control flow (descriptors live in uniform registers);
