@@ -58,6 +58,20 @@ int make_map_thd(CUtensorMap* m, const void* ptr, int dtype, int tokens, int hea
   return 0;
 }
 
+// fp32 [tokens, heads, 128] accumulator -> 3-D map (d, h, t), box (32, 1, 128), SWIZZLE_128B (TMA reduce-add target)
+int make_map_f32_acc(CUtensorMap* m, void* ptr, int tokens, int heads, int64_t stride_t, int64_t stride_h, const char* what) {
+  EncodeTiled_t enc = get_encode();
+  if (!enc) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {cuuint64_t(ffa::kHeadDim), cuuint64_t(heads), cuuint64_t(tokens)};
+  cuuint64_t strides[2] = {cuuint64_t(stride_h) * 4, cuuint64_t(stride_t) * 4};
+  cuuint32_t box[3] = {32, 1, 128};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed (%d)", what, int(r));
+  return 0;
+}
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int check_common(int dtype, int hq, int hk, int d, float softcap) {
@@ -205,7 +219,7 @@ int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream_) {
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "bwd preprocess launch: %s", cudaGetErrorString(e));
   ++g_launches;
 
-  CUtensorMap tmQ, tmDO, tmK, tmV;
+  CUtensorMap tmQ, tmDO, tmK, tmV, tmDQ;
   const bool q_empty = p->total_q == 0;
   if (int rc = make_map_thd(&tmQ, q_empty ? p->k : p->q, p->dtype, q_empty ? 1 : p->total_q, q_empty ? p->num_heads_kv : p->num_heads_q,
                             q_empty ? p->k_stride_t : p->q_stride_t, q_empty ? p->k_stride_h : p->q_stride_h, 128, "q")) return rc;
@@ -213,6 +227,11 @@ int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream_) {
                             q_empty ? p->k_stride_t : p->do_stride_t, q_empty ? p->k_stride_h : p->do_stride_h, 128, "dout")) return rc;
   if (int rc = make_map_thd(&tmK, p->k, p->dtype, p->total_k, p->num_heads_kv, p->k_stride_t, p->k_stride_h, 128, "k")) return rc;
   if (int rc = make_map_thd(&tmV, p->v, p->dtype, p->total_k, p->num_heads_kv, p->v_stride_t, p->v_stride_h, 128, "v")) return rc;
+  if (q_empty) {
+    tmDQ = tmK;  // never used: no q block is ever visited
+  } else if (int rc = make_map_f32_acc(&tmDQ, p->dq, p->total_q, p->num_heads_q, p->dq_stride_t, p->dq_stride_h, "dq")) {
+    return rc;
+  }
 
   ffa::BwdArgs a{};
   a.meta = meta;
@@ -236,7 +255,7 @@ int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream_) {
   a.dv_stride_h = p->dv_stride_h;
   a.scale = p->softmax_scale;
   a.accumulate_dkv = p->accumulate_dkv;
-  e = ffa::launch_bwd(p->dtype == B200_BF16, p->dkv_dtype == B200_F32, tmQ, tmDO, tmK, tmV, a, stream);
+  e = ffa::launch_bwd(p->dtype == B200_BF16, p->dkv_dtype == B200_F32, tmQ, tmDO, tmK, tmV, tmDQ, a, stream);
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "bwd launch: %s", cudaGetErrorString(e));
   ++g_launches;
   return 0;

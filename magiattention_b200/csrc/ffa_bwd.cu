@@ -34,10 +34,13 @@ namespace bwd {
 constexpr int kThreads = 512;
 constexpr uint32_t kTileBytes = 128 * 128 * 2;
 constexpr uint32_t kBoxBytes = kTileBytes / 2;
+// K, V resident; dS^T staging; Q double-buffered; dO single-buffered (its next load is issued as soon as dV
+// retires, ~1.5k clocks before dP needs it); two 16 KB staging buffers for the TMA reduce-add of dQ.
 constexpr uint32_t kSmemK = 0, kSmemV = kTileBytes, kSmemDS = 2 * kTileBytes, kSmemQ = 3 * kTileBytes,
-                   kSmemDO = 5 * kTileBytes, kSmemLse = 7 * kTileBytes, kSmemDelta = kSmemLse + 1024,
-                   kSmemBar = kSmemDelta + 1024, kSmemBytes = kSmemBar + 256;
-constexpr int kBarKV = 0, kBarQFull = 1, kBarQEmpty = 3, kBarDOFull = 5, kBarDOEmpty = 7, kBarS = 9, kBarDP = 10,
+                   kSmemDO = 5 * kTileBytes, kSmemDQ = 6 * kTileBytes, kSmemLse = 7 * kTileBytes,
+                   kSmemDelta = kSmemLse + 1024, kSmemBar = kSmemDelta + 1024, kSmemBytes = kSmemBar + 256;
+constexpr uint32_t kDQChunkBytes = 128 * 32 * 4;
+constexpr int kBarKV = 0, kBarQFull = 1, kBarQEmpty = 3, kBarDOFull = 5, kBarDOEmpty = 6, kBarS = 9, kBarDP = 10,
               kBarP = 11, kBarDS = 12, kBarDQ = 13, kBarDrained = 14, kBarDKV = 15, kNumBars = 16;
 constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 384;
 }  // namespace bwd
@@ -123,7 +126,8 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 template <bool kBF16, bool kDkvF32>
 __global__ void __launch_bounds__(bwd::kThreads, 1)
 ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
-               const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const BwdArgs args) {
+               const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+               const __grid_constant__ CUtensorMap tmDQ, const BwdArgs args) {
   using namespace bwd;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
@@ -159,6 +163,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     prefetch_tmap(&tmDO);
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
+    prefetch_tmap(&tmDQ);
   }
   tc_fence_before();
   __syncthreads();
@@ -322,11 +327,17 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else if (wid < 12) {
     // ================================ dQ drain warpgroup ================================
+    // dQ tile (128 q rows x 128 d, fp32) : TMEM -> registers (x scale) -> 128B-swizzled smem chunk of 32 columns
+    // -> cp.reduce.async.bulk.tensor (TMA reduce-add into the fp32 global dq).  The TMA engine does the L2
+    // reductions in full lines; the SM only pays 8 st.shared.v4 per thread per chunk.
     setmaxnreg_dec<96>();
     const uint32_t lane_off = uint32_t((wid & 3) * 32) << 16;
     const uint32_t tDQ = tmem + lane_off + kTmemDP;
     const int qrow_in_blk = (wid & 3) * 32 + lane;
-    uint32_t it = 0;
+    const int dtid = tid - 256;  // 0..127 inside the drain warpgroup
+    uint8_t* stage_row = smem + kSmemDQ + qrow_in_blk * 128;
+    const int swz = qrow_in_blk & 7;
+    uint32_t it = 0, chunk_ctr = 0;
     for (int g = 0; g < G; ++g) {
       const int hq = hk * G + g;
       SliceCursor cur;
@@ -336,43 +347,39 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       while (cur.next(sl)) {
         if (!gm.init(sl, C0)) continue;
         for (int b = 0; b < gm.nblk; ++b, ++it) {
-          const int row = gm.r_start + b * kBlockM + qrow_in_blk;
-          const bool live = (row >= gm.r_min) && (row < gm.r_max);  // rows outside the hull hold exact zeros
-          float* dq = args.dq + int64_t(row) * args.dq_stride_t + int64_t(hq) * args.dq_stride_h;
+          const int rs = gm.r_start + b * kBlockM;
           mbar_wait(bar(kBarDQ), it & 1);
           tc_fence_after();
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            uint32_t r0[32], r1[32];
-            tmem_ld32(tDQ + hf * 64, r0);
-            tmem_ld32(tDQ + hf * 64 + 32, r1);
+          for (int c = 0; c < 4; ++c, ++chunk_ctr) {
+            uint32_t r[32];
+            tmem_ld32(tDQ + c * 32, r);
             tc_wait_ld();
-            if (hf == 1) {
+            if (c == 3) {
               tc_fence_before();
-              mbar_arrive(bar(kBarDrained));
+              mbar_arrive(bar(kBarDrained));  // TMEM dQ region may be overwritten by the next dP
             }
-            if (live) {
+            const uint32_t buf = chunk_ctr & 1;
+            if (dtid == 0) tma_store_wait_read<1>();  // the reduce that last read this buffer has consumed it
+            named_bar_sync(1, 128);
+            uint8_t* dst = stage_row + buf * kDQChunkBytes;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float* p0 = dq + hf * 64 + i * 4;
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p0),
-                             "f"(__uint_as_float(r0[4 * i]) * args.scale), "f"(__uint_as_float(r0[4 * i + 1]) * args.scale),
-                             "f"(__uint_as_float(r0[4 * i + 2]) * args.scale), "f"(__uint_as_float(r0[4 * i + 3]) * args.scale)
-                             : "memory");
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float* p1 = dq + hf * 64 + 32 + i * 4;
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p1),
-                             "f"(__uint_as_float(r1[4 * i]) * args.scale), "f"(__uint_as_float(r1[4 * i + 1]) * args.scale),
-                             "f"(__uint_as_float(r1[4 * i + 2]) * args.scale), "f"(__uint_as_float(r1[4 * i + 3]) * args.scale)
-                             : "memory");
-              }
+            for (int j = 0; j < 8; ++j) {
+              *reinterpret_cast<float4*>(dst + ((j ^ swz) << 4)) =
+                  make_float4(__uint_as_float(r[4 * j]) * args.scale, __uint_as_float(r[4 * j + 1]) * args.scale,
+                              __uint_as_float(r[4 * j + 2]) * args.scale, __uint_as_float(r[4 * j + 3]) * args.scale);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (dtid == 0) {
+              tma_reduce_add_3d(&tmDQ, smem_base + kSmemDQ + buf * kDQChunkBytes, c * 32, hq, rs);
+              tma_store_commit();
             }
           }
         }
       }
     }
+    if (dtid == 0) tma_store_wait<0>();
   } else {
     setmaxnreg_dec<96>();
     if (wid == 12) {
@@ -425,17 +432,17 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mbar_wait(bar(kBarQFull + 0), 0);
           tc_fence_after();
           mma_kmajor(tS, sK, smem_base + kSmemQ, bar(kBarS));
-          mbar_wait(bar(kBarDOFull + 0), 0);
+          mbar_wait(bar(kBarDOFull), 0);
           tc_fence_after();
           mma_kmajor(tDP, sV, smem_base + kSmemDO, bar(kBarDP));
           for (uint32_t it = 0; it < n_it; ++it) {
             const uint32_t st = it & 1, nst = st ^ 1;
-            const uint32_t sQ = smem_base + kSmemQ + st * kTileBytes, sDO = smem_base + kSmemDO + st * kTileBytes;
+            const uint32_t sQ = smem_base + kSmemQ + st * kTileBytes, sDO = smem_base + kSmemDO;
             const bool has_next = it + 1 < n_it;
             // dV += P^T dO
             mbar_wait(bar(kBarP), it & 1);
             tc_fence_after();
-            mma_tmemA(tDV, tS, sDO, it > 0, bar(kBarDOEmpty + st));  // dO_it no longer needed once dV retires
+            mma_tmemA(tDV, tS, sDO, it > 0, bar(kBarDOEmpty));  // dO_it no longer needed once dV retires
             // S_{it+1} (S region is free after dV in tensor-pipe order)
             if (has_next) {
               mbar_wait(bar(kBarQFull + nst), ((it + 1) >> 1) & 1);
@@ -456,9 +463,9 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             // dP_{it+1} once the dQ tile has been drained out of the shared TMEM region
             if (has_next) {
               mbar_wait(bar(kBarDrained), it & 1);
-              mbar_wait(bar(kBarDOFull + nst), ((it + 1) >> 1) & 1);
+              mbar_wait(bar(kBarDOFull), (it + 1) & 1);
               tc_fence_after();
-              mma_kmajor(tDP, sV, smem_base + kSmemDO + nst * kTileBytes, bar(kBarDP));
+              mma_kmajor(tDP, sV, smem_base + kSmemDO, bar(kBarDP));
             }
           }
           if (elect_one()) tc_commit(bar(kBarDKV));
@@ -504,12 +511,12 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 bulk_load(smem_base + kSmemDelta + st * 512, delta + rs, 512, bar(kBarQFull + st));
               }
               __syncwarp();
-              mbar_wait(bar(kBarDOEmpty + st), ph ^ 1);
+              mbar_wait(bar(kBarDOEmpty), (it & 1) ^ 1);
               if (elect_one()) {
-                mbar_arrive_expect_tx(bar(kBarDOFull + st), kTileBytes);
-                const uint32_t sDO = smem_base + kSmemDO + st * kTileBytes;
-                tma_load_3d(sDO, &tmDO, bar(kBarDOFull + st), 0, hq, rs);
-                tma_load_3d(sDO + kBoxBytes, &tmDO, bar(kBarDOFull + st), 64, hq, rs);
+                mbar_arrive_expect_tx(bar(kBarDOFull), kTileBytes);
+                const uint32_t sDO = smem_base + kSmemDO;
+                tma_load_3d(sDO, &tmDO, bar(kBarDOFull), 0, hq, rs);
+                tma_load_3d(sDO + kBoxBytes, &tmDO, bar(kBarDOFull), 64, hq, rs);
               }
               __syncwarp();
             }
@@ -547,7 +554,8 @@ cudaError_t launch_bwd_preprocess(bool bf16, const void* out, const void* dout, 
 
 template <bool kBF16, bool kDkvF32>
 static cudaError_t launch_bwd_one(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK,
-                                  const CUtensorMap& tmV, const BwdArgs& a, int grid, cudaStream_t stream) {
+                                  const CUtensorMap& tmV, const CUtensorMap& tmDQ, const BwdArgs& a, int grid,
+                                  cudaStream_t stream) {
   auto kern = ffa_bwd_kernel<kBF16, kDkvF32>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -555,18 +563,18 @@ static cudaError_t launch_bwd_one(const CUtensorMap& tmQ, const CUtensorMap& tmD
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, bwd::kThreads, bwd::kSmemBytes, stream>>>(tmQ, tmDO, tmK, tmV, a);
+  kern<<<grid, bwd::kThreads, bwd::kSmemBytes, stream>>>(tmQ, tmDO, tmK, tmV, tmDQ, a);
   return cudaGetLastError();
 }
 
 cudaError_t launch_bwd(bool bf16, bool dkv_f32, const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK,
-                       const CUtensorMap& tmV, const BwdArgs& a, cudaStream_t stream) {
+                       const CUtensorMap& tmV, const CUtensorMap& tmDQ, const BwdArgs& a, cudaStream_t stream) {
   const int grid = a.n_tiles * a.num_heads_kv;
   if (grid == 0) return cudaSuccess;
-  if (bf16) return dkv_f32 ? launch_bwd_one<true, true>(tmQ, tmDO, tmK, tmV, a, grid, stream)
-                           : launch_bwd_one<true, false>(tmQ, tmDO, tmK, tmV, a, grid, stream);
-  return dkv_f32 ? launch_bwd_one<false, true>(tmQ, tmDO, tmK, tmV, a, grid, stream)
-                 : launch_bwd_one<false, false>(tmQ, tmDO, tmK, tmV, a, grid, stream);
+  if (bf16) return dkv_f32 ? launch_bwd_one<true, true>(tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream)
+                           : launch_bwd_one<true, false>(tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream);
+  return dkv_f32 ? launch_bwd_one<false, true>(tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream)
+                 : launch_bwd_one<false, false>(tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream);
 }
 
 }  // namespace ffa

@@ -16,5 +16,5 @@ cudaError_t launch_bwd_preprocess(bool bf16, const void* out, const void* dout, 
                                   int64_t o_stride_h, int64_t do_stride_t, int64_t do_stride_h, int64_t lse_stride_t,
                                   int64_t lse_stride_h, cudaStream_t stream);
 cudaError_t launch_bwd(bool bf16, bool dkv_f32, const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK,
-                       const CUtensorMap& tmV, const BwdArgs& a, cudaStream_t stream);
+                       const CUtensorMap& tmV, const CUtensorMap& tmDQ, const BwdArgs& a, cudaStream_t stream);
 }  // namespace ffa
