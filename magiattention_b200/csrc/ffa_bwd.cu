@@ -350,30 +350,37 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const int rs = gm.r_start + b * kBlockM;
           mbar_wait(bar(kBarDQ), it & 1);
           tc_fence_after();
+          // two halves of 64 columns: the TMEM region is released (kBarDrained) as soon as the second half sits
+          // in registers, i.e. after staging only the first half
 #pragma unroll
-          for (int c = 0; c < 4; ++c, ++chunk_ctr) {
-            uint32_t r[32];
-            tmem_ld32(tDQ + c * 32, r);
+          for (int h2 = 0; h2 < 2; ++h2) {
+            uint32_t r[2][32];
+            tmem_ld32(tDQ + h2 * 64, r[0]);
+            tmem_ld32(tDQ + h2 * 64 + 32, r[1]);
             tc_wait_ld();
-            if (c == 3) {
+            if (h2 == 1) {
               tc_fence_before();
               mbar_arrive(bar(kBarDrained));  // TMEM dQ region may be overwritten by the next dP
             }
-            const uint32_t buf = chunk_ctr & 1;
-            if (dtid == 0) tma_store_wait_read<1>();  // the reduce that last read this buffer has consumed it
-            named_bar_sync(1, 128);
-            uint8_t* dst = stage_row + buf * kDQChunkBytes;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              *reinterpret_cast<float4*>(dst + ((j ^ swz) << 4)) =
-                  make_float4(__uint_as_float(r[4 * j]) * args.scale, __uint_as_float(r[4 * j + 1]) * args.scale,
-                              __uint_as_float(r[4 * j + 2]) * args.scale, __uint_as_float(r[4 * j + 3]) * args.scale);
-            }
-            fence_proxy_async_smem();
-            named_bar_sync(1, 128);
-            if (dtid == 0) {
-              tma_reduce_add_3d(&tmDQ, smem_base + kSmemDQ + buf * kDQChunkBytes, c * 32, hq, rs);
-              tma_store_commit();
+            for (int cc = 0; cc < 2; ++cc, ++chunk_ctr) {
+              const int c = h2 * 2 + cc;
+              const uint32_t buf = chunk_ctr & 1;
+              if (dtid == 0) tma_store_wait_read<1>();  // the reduce that last read this buffer has consumed it
+              named_bar_sync(1, 128);
+              uint8_t* dst = stage_row + buf * kDQChunkBytes;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                *reinterpret_cast<float4*>(dst + ((j ^ swz) << 4)) = make_float4(
+                    __uint_as_float(r[cc][4 * j]) * args.scale, __uint_as_float(r[cc][4 * j + 1]) * args.scale,
+                    __uint_as_float(r[cc][4 * j + 2]) * args.scale, __uint_as_float(r[cc][4 * j + 3]) * args.scale);
+              }
+              fence_proxy_async_smem();
+              named_bar_sync(1, 128);
+              if (dtid == 0) {
+                tma_reduce_add_3d(&tmDQ, smem_base + kSmemDQ + buf * kDQChunkBytes, c * 32, hq, rs);
+                tma_store_commit();
+              }
             }
           }
         }
