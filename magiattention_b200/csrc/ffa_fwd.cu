@@ -46,7 +46,7 @@ constexpr uint32_t kSmemBar = kSmemKV + kStages * kTileBytes;
 constexpr uint32_t kSmemBytes = kSmemBar + 256;
 // barrier indices
 constexpr int kBarQ = 0, kBarFull = 1, kBarEmpty = kBarFull + kStages, kBarS = kBarEmpty + kStages, kBarP = kBarS + 2,
-              kBarO = kBarP + 2, kNumBars = kBarO + 2;
+              kBarPhi = kBarP + 2, kBarO = kBarPhi + 2, kNumBars = kBarO + 2;  // kBarP: first half of P, kBarPhi: second
 static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
 constexpr uint32_t kTmemS = 0, kTmemO = 256;
 constexpr float kRescaleThreshold = 8.0f;
@@ -82,6 +82,37 @@ struct TileGeom {
   __device__ __forceinline__ bool active(int bs) const { return act && (bs + kBlockN > ct_min) && (bs < ct_max); }
   __device__ __forceinline__ bool full(int bs) const { return rows_full && full_lo <= bs && bs + kBlockN <= full_hi; }
 };
+
+// exp2 of 64 scores of one row (stale-or-fresh reference max folded into `mneg`), packed 16-bit P written to
+// 32 TMEM columns starting at `t_dst`; returns the two partial row sums.  kEmuCount of every kEmuPeriod pairs go
+// through the FMA-pipe polynomial, the rest through MUFU.EX2.
+template <bool kBF16>
+__device__ __forceinline__ float2 softmax_half(const uint32_t* sr, float sl2, float mneg, uint32_t t_dst) {
+  using namespace fwd;
+  const float2 sl2_2 = make_float2(sl2, sl2), mneg2 = make_float2(mneg, mneg);
+  float2 acc4[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t pr[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[32 * c + 2 * i]), __uint_as_float(sr[32 * c + 2 * i + 1])),
+                                  sl2_2, mneg2);
+      float2 pv;
+      if ((i % kEmuPeriod) < kEmuCount) {
+        pv = ex2_emu2<kEmuDegree>(x);
+      } else {
+        pv.x = ex2(x.x);
+        pv.y = ex2(x.y);
+      }
+      acc4[i & 3] = __fadd2_rn(acc4[i & 3], pv);
+      pr[i] = pack2<kBF16>(pv.x, pv.y);
+    }
+    tmem_st16(t_dst + c * 16, pr);
+  }
+  const float2 a01 = __fadd2_rn(acc4[0], acc4[1]), a23 = __fadd2_rn(acc4[2], acc4[3]);
+  return __fadd2_rn(a01, a23);
+}
 
 template <bool kBF16, bool kOutF32>
 __global__ void __launch_bounds__(fwd::kThreads, 1)
@@ -120,6 +151,7 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar(kBarS + t), 1);
       mbar_init(bar(kBarP + t), 128);
+      mbar_init(bar(kBarPhi + t), 128);
       mbar_init(bar(kBarO + t), 1);
     }
     fence_barrier_init();
@@ -184,9 +216,12 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               if (!((bits >> i) & 1u)) sr[c * 32 + i] = 0xff800000u;  // -inf
           }
         }
+        // Block max on 4 independent chains.  Nothing below depends on it until the validity check, so the
+        // scheduler overlaps it with the first half of the exponentials, which use the STALE reference max:
+        // with lazy rescaling the reference only has to be within 2^8 of the true max, which the check verifies.
         float mb;
         {
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent 3-input-max chains
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
           for (int i = 0; i < 128; i += 8) {
 #pragma unroll
@@ -195,78 +230,41 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           mb = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         }
+        float mneg = (m_ref == -INFINITY) ? 0.f : -m_ref * sl2;
+        float2 acc_lo = softmax_half<kBF16>(&sr[0], sl2, mneg, tS);
         const float m_new = fmaxf(m_ref, mb);
         const bool upd = (m_new - m_ref) * sl2 > kRescaleThreshold;  // NaN (-inf - -inf) compares false
-        float corr = 1.f;
-        if (upd) {
-          corr = (m_ref == -INFINITY) ? 0.f : ex2((m_ref - m_new) * sl2);
-          m_ref = m_new;
-          l_sum *= corr;
-        }
-        if (n_act > 0 && __any_sync(0xffffffffu, upd)) {
-          // rescale O (PV of the previous block has completed: its commit preceded S(cur)'s)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tO + c * 32, o);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
-            tmem_st32(tO + c * 32, o);
+        if (__any_sync(0xffffffffu, upd)) {
+          // slow path (first block of a tile, or the running max grew by more than 2^8): move the reference,
+          // rescale O (PV of the previous block has completed: its commit preceded S(cur)'s), redo the half.
+          float corr = 1.f;
+          if (upd) {
+            corr = (m_ref == -INFINITY) ? 0.f : ex2((m_ref - m_new) * sl2);
+            m_ref = m_new;
+            l_sum *= corr;
           }
-        }
-        const float mneg = (m_ref == -INFINITY) ? 0.f : -m_ref * sl2;
-#if FFA_FWD_PACKED
-        const float2 sl2_2 = make_float2(sl2, sl2), mneg2 = make_float2(mneg, mneg);
-        float2 acc4[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+          if (n_act > 0) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pr[16];
+            for (int c = 0; c < 4; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 x = __ffma2_rn(make_float2(__uint_as_float(sr[32 * c + 2 * i]), __uint_as_float(sr[32 * c + 2 * i + 1])),
-                                        sl2_2, mneg2);
-            float2 pv;
-            if ((i % kEmuPeriod) < kEmuCount) {
-              pv = ex2_emu2<kEmuDegree>(x);
-            } else {
-              pv.x = ex2(x.x);
-              pv.y = ex2(x.y);
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+              tmem_st32(tO + c * 32, o);
             }
-            acc4[i & 3] = __fadd2_rn(acc4[i & 3], pv);
-            pr[i] = pack2<kBF16>(pv.x, pv.y);
           }
-          tmem_st16(tS + c * 16, pr);
+          mneg = (m_ref == -INFINITY) ? 0.f : -m_ref * sl2;
+          acc_lo = softmax_half<kBF16>(&sr[0], sl2, mneg, tS);
         }
-        {
-          const float2 a01 = __fadd2_rn(acc4[0], acc4[1]), a23 = __fadd2_rn(acc4[2], acc4[3]);
-          l_sum += (a01.x + a01.y) + (a23.x + a23.y);
-        }
-#else
-        float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pr[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0 = fmaf(__uint_as_float(sr[32 * c + 2 * i]), sl2, mneg);
-            float p1 = fmaf(__uint_as_float(sr[32 * c + 2 * i + 1]), sl2, mneg);
-            if ((i % kEmuPeriod) < kEmuCount) {
-              const float2 pv = ex2_emu2<kEmuDegree>(make_float2(p0, p1));
-              p0 = pv.x; p1 = pv.y;
-            } else {
-              p0 = ex2(p0); p1 = ex2(p1);
-            }
-            acc0 += p0; acc1 += p1;
-            pr[i] = pack2<kBF16>(p0, p1);
-          }
-          tmem_st16(tS + c * 16, pr);
-        }
-        l_sum += acc0 + acc1;
-#endif
         tc_wait_st();
         tc_fence_before();
-        mbar_arrive(bar(kBarP + t));
+        mbar_arrive(bar(kBarP + t));  // P[:, 0:64) (and any O rescale) visible: first 4 PV k-steps may start
+        const float2 acc_hi = softmax_half<kBF16>(&sr[64], sl2, mneg, tS + 32);
+        l_sum += (acc_lo.x + acc_lo.y) + (acc_hi.x + acc_hi.y);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar(kBarPhi + t));
         ++n_act;
       }
     }
@@ -387,18 +385,26 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       bool q_ready = false;
 
       auto issue_pv = [&](const int t, const uint32_t n_act_t, const uint32_t li) {
-        mbar_wait(bar(kBarP + t), (n_act_t - 1) & 1);  // P_t of the pending block is in TMEM
         const uint32_t buf = li % kStages;
-        mbar_wait(bar(kBarFull + buf), (li / kStages) & 1);
-        tc_fence_after();
         const uint32_t sV = sKV + buf * kTileBytes;
         const uint32_t tP = tmem + kTmemS + t * 128, tOt = tmem + kTmemO + t * 128;
+        mbar_wait(bar(kBarFull + buf), (li / kStages) & 1);
+        mbar_wait(bar(kBarP + t), (n_act_t - 1) & 1);  // first 64 columns of P_t are in TMEM
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (uint32_t kk = 0; kk < 4; ++kk)
+            mma_ts(tOt, tP + kk * 8, smem_desc(desc_v_hi, sV + kk * 2048), idesc_pv, (n_act_t > 1 || kk > 0) ? 1u : 0u);
+        }
+        __syncwarp();
+        mbar_wait(bar(kBarPhi + t), (n_act_t - 1) & 1);  // second half
+        tc_fence_after();
         pend -= 1u << (4 * buf);
         const bool release = ((pend >> (4 * buf)) & 15u) == 0;
         if (elect_one()) {
 #pragma unroll
-          for (uint32_t kk = 0; kk < 8; ++kk)
-            mma_ts(tOt, tP + kk * 8, smem_desc(desc_v_hi, sV + kk * 2048), idesc_pv, (n_act_t > 1 || kk > 0) ? 1u : 0u);
+          for (uint32_t kk = 4; kk < 8; ++kk)
+            mma_ts(tOt, tP + kk * 8, smem_desc(desc_v_hi, sV + kk * 2048), idesc_pv, 1u);
           if (release) tc_commit(bar(kBarEmpty + buf));
         }
         __syncwarp();
