@@ -208,3 +208,60 @@ def test_full_size_properties_c2_like():
         lo, ll = orc.attn_fwd(q[sub], k[sub], v[sub], mask, high_precision=False)
         orc.check_close("out", o1[sub], ro, lo, "out")
         orc.check_close("lse", m1.lse[sub], rl, ll, "lse")
+
+
+def test_plan_overflow_falls_back_to_slice_scan():
+    """With a workspace too small for the tile->slice CSR the kernels must scan all slices instead (same results)."""
+    import ctypes as C
+    from magiattention_b200 import _lib
+
+    dev = _dev()
+    torch.manual_seed(9)
+    cfg = next(c for c in mask_configs(1) if c["name"] == "sparse_attn_2k")
+    T, H = cfg["seqlen"], 2
+    q, k, v = (torch.randn(T, H, D, dtype=torch.bfloat16, device=dev) for _ in range(3))
+    mk = lambda r: torch.tensor(r, dtype=torch.int32, device=dev).reshape(-1, 2)
+    qr, kr, ty = mk(cfg["q_ranges"]), mk(cfg["k_ranges"]), torch.tensor(cfg["types"], dtype=torch.int32, device=dev)
+    out_ref = torch.empty_like(q)
+    lse_ref = torch.empty(T, H, dtype=torch.float32, device=dev)
+    _lib.ffa_fwd(q, k, v, out_ref, lse_ref, qr, kr, ty, D ** -0.5)
+    # same call through the raw ABI with a workspace that only fits the CSR header + offsets
+    p = _lib.FwdParams()
+    out = torch.empty_like(q)
+    lse = torch.empty(T, H, dtype=torch.float32, device=dev)
+    p.q, p.k, p.v, p.out, p.lse = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr()
+    p.q_ranges, p.k_ranges, p.attn_type_map, p.num_slices = qr.data_ptr(), kr.data_ptr(), ty.data_ptr(), qr.shape[0]
+    p.total_q = p.total_k = T
+    p.num_heads_q = p.num_heads_kv = H
+    p.head_dim = D
+    for n, t in (("q", q), ("k", k), ("v", v), ("o", out)):
+        setattr(p, f"{n}_stride_t", t.stride(0)); setattr(p, f"{n}_stride_h", t.stride(1))
+    p.lse_stride_t, p.lse_stride_h = lse.stride(0), lse.stride(1)
+    p.softmax_scale, p.dtype, p.out_dtype = D ** -0.5, _lib.B200_BF16, _lib.B200_BF16
+    ws = torch.empty(1024, dtype=torch.uint8, device=dev)  # << b200_ffa_fwd_workspace_bytes
+    assert ws.numel() < _lib.lib().b200_ffa_fwd_workspace_bytes(C.byref(p))
+    p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    rc = _lib.lib().b200_ffa_fwd(C.byref(p), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, _lib.lib().b200_ffa_last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(out, out_ref) and torch.equal(lse, lse_ref)
+
+
+def test_strided_inputs_packed_qkv():
+    """q/k/v as views into one packed [T, 3, H, D] tensor (token stride 3*H*D): the TMA maps carry the strides."""
+    from magiattention_b200 import _lib
+
+    dev = _dev()
+    torch.manual_seed(10)
+    T, H = 777, 2
+    qkv = torch.randn(T, 3, H, D, dtype=torch.bfloat16, device=dev)
+    q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]
+    r = torch.tensor([[0, T]], dtype=torch.int32, device=dev)
+    ty = torch.tensor([1], dtype=torch.int32, device=dev)
+    out = torch.empty(T, H, D, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(T, H, dtype=torch.float32, device=dev)
+    _lib.ffa_fwd(q, k, v, out, lse, r, r, ty, D ** -0.5)
+    out2 = torch.empty_like(out)
+    lse2 = torch.empty_like(lse)
+    _lib.ffa_fwd(q.contiguous(), k.contiguous(), v.contiguous(), out2, lse2, r, r, ty, D ** -0.5)
+    assert torch.equal(out, out2) and torch.equal(lse, lse2)
