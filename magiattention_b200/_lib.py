@@ -14,7 +14,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200_ffa.so")
+# B200_FFA_LIB lets a developer point at an alternative build of the same library (kernel tuning variants)
+LIB_PATH = os.environ.get("B200_FFA_LIB") or os.path.join(_HERE, "lib", "libb200_ffa.so")
 
 B200_F16, B200_BF16, B200_F32 = 0, 1, 2
 _DT = {torch.float16: B200_F16, torch.bfloat16: B200_BF16, torch.float32: B200_F32}

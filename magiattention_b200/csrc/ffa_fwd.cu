@@ -51,7 +51,10 @@ static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
 constexpr uint32_t kTmemS = 0, kTmemO = 256;
 constexpr float kRescaleThreshold = 8.0f;
 // exp2 on the FMA pipe for kEmuCount of every kEmuPeriod element pairs (rest on the SFU)
-constexpr int kEmuPeriod = 8, kEmuCount = 3, kEmuDegree = 4;
+#ifndef FFA_EMU_COUNT
+#define FFA_EMU_COUNT 2
+#endif
+constexpr int kEmuPeriod = 8, kEmuCount = FFA_EMU_COUNT, kEmuDegree = 4;
 }  // namespace fwd
 
 

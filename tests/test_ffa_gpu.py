@@ -238,7 +238,7 @@ def test_plan_overflow_falls_back_to_slice_scan():
         setattr(p, f"{n}_stride_t", t.stride(0)); setattr(p, f"{n}_stride_h", t.stride(1))
     p.lse_stride_t, p.lse_stride_h = lse.stride(0), lse.stride(1)
     p.softmax_scale, p.dtype, p.out_dtype = D ** -0.5, _lib.B200_BF16, _lib.B200_BF16
-    ws = torch.empty(1024, dtype=torch.uint8, device=dev)  # << b200_ffa_fwd_workspace_bytes
+    ws = torch.empty(320, dtype=torch.uint8, device=dev)  # header + offsets + room for only 16 CSR entries
     assert ws.numel() < _lib.lib().b200_ffa_fwd_workspace_bytes(C.byref(p))
     p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
     rc = _lib.lib().b200_ffa_fwd(C.byref(p), torch.cuda.current_stream().cuda_stream)
@@ -265,3 +265,25 @@ def test_strided_inputs_packed_qkv():
     lse2 = torch.empty_like(lse)
     _lib.ffa_fwd(q.contiguous(), k.contiguous(), v.contiguous(), out2, lse2, r, r, ty, D ** -0.5)
     assert torch.equal(out, out2) and torch.equal(lse, lse2)
+
+
+def test_baseline_config_c1():
+    """BASELINE.json configs[0]: single-GPU fwd, seq=4096, nheads=16, d=128, full-causal, bf16 — area 8 390 656."""
+    qr = kr = [[0, 4096]]
+    assert orc.mask_area(qr, kr, [1]) == 8390656
+    _run_case(qr, kr, [1], 4096, 4096, 16, 16, torch.bfloat16, check_bwd=False)
+
+
+def test_block_sparse_gqa_c5_like():
+    """C5-like (scaled): GQA 8:1, video-gen style varlen block-causal rectangles — each q block attends its own
+    block, the previous two blocks and the global first block — as FULL slices; fwd + bwd."""
+    torch.manual_seed(12)
+    edges = [0, 300, 812, 1324, 1580, 2604, 3116, 3500, 4096]
+    qr, kr = [], []
+    for i in range(len(edges) - 1):
+        q = [edges[i], edges[i + 1]]
+        lo = max(i - 2, 0)
+        qr.append(q); kr.append([edges[lo], edges[i + 1]])
+        if lo > 0:
+            qr.append(q); kr.append([edges[0], edges[1]])
+    _run_case(qr, kr, [0] * len(qr), 4096, 4096, 8, 1, torch.bfloat16)

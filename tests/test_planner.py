@@ -152,3 +152,24 @@ def test_sliding_window_inference_known_answer():
     doc = torch.bucketize(torch.arange(8192), torch.tensor([3000, 3500, 8192]), right=True)
     want = (doc.unsqueeze(1) == doc.unsqueeze(0)) & (j <= i) & (j >= i - 1024)
     assert torch.equal(m, want)
+
+
+def test_planner_block_sparse_many_slices():
+    """C5-like (scaled down): varlen block-causal rectangles (own block + previous two + global first block), cp=8."""
+    import random
+
+    random.seed(3)
+    T, cp, chunk = 2048, 8, 16
+    edges = [0]
+    while edges[-1] < T:
+        edges.append(min(T, edges[-1] + random.choice([16, 32, 48, 64, 96])))
+    sl = []
+    for i in range(len(edges) - 1):
+        lo = max(i - 2, 0)
+        sl.append((edges[i], edges[i + 1], edges[lo], edges[i + 1], 0))
+        if lo > 0:
+            sl.append((edges[i], edges[i + 1], edges[0], edges[1], 0))
+    dm, comm, calc = _simulate(sl, T, cp, chunk, 2, H=2, HK=1, D=8)
+    # zero-redundancy: nobody fetches more remote rows than exist outside its shard
+    for r in range(cp):
+        assert sum(comm[r].num_remote_kv_tokens_per_stage) <= T - dm.shard_seqlen
