@@ -50,9 +50,11 @@ constexpr int kBarQ = 0, kBarFull = 1, kBarEmpty = kBarFull + kStages, kBarS = k
 static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
 constexpr uint32_t kTmemS = 0, kTmemO = 256;
 constexpr float kRescaleThreshold = 8.0f;
-// exp2 on the FMA pipe for kEmuCount of every kEmuPeriod element pairs (rest on the SFU)
+// exp2 on the FMA pipe for kEmuCount of every kEmuPeriod element pairs (rest on the SFU).  Measured on B200
+// (causal 32K x 8 heads, after the issue-loop fixes): 0/8 -> 1288, 1/8 -> 1258, 2/8 -> 1231, 3/8 -> 1191, 4/8 -> 1105
+// TFLOP/s: with packed FFMA2/FADD2 the kernel is issue/latency-bound, not MUFU-bound, so the default is 0.
 #ifndef FFA_EMU_COUNT
-#define FFA_EMU_COUNT 2
+#define FFA_EMU_COUNT 0
 #endif
 constexpr int kEmuPeriod = 8, kEmuCount = FFA_EMU_COUNT, kEmuDegree = 4;
 }  // namespace fwd
