@@ -6,7 +6,11 @@
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#ifndef FFA_FWD_DEFAULT_VARIANT
+#define FFA_FWD_DEFAULT_VARIANT 128
+#endif
 #include "../../include/b200_ffa.h"
 #include "ffa_args.h"
 #include "ffa_kernels.h"
@@ -74,6 +78,16 @@ int make_map_f32_acc(CUtensorMap* m, void* ptr, int tokens, int heads, int64_t s
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// forward kernel variant: 64 (default: 64-column kv blocks, double-buffered S) or 128 (B200_FFA_FWD_VARIANT=128)
+int fwd_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200_FFA_FWD_VARIANT");
+    v = (e && atoi(e) == 128) ? 128 : (e && atoi(e) == 64) ? 64 : FFA_FWD_DEFAULT_VARIANT;
+  }
+  return v;
+}
+
 int check_common(int dtype, int hq, int hk, int d, float softcap) {
   if (dtype != B200_F16 && dtype != B200_BF16) return fail(B200_ERR_INVALID, "dtype must be f16 or bf16");
   if (d != ffa::kHeadDim) return fail(B200_ERR_UNSUPPORTED, "head_dim %d unsupported (only 128)", d);
@@ -131,10 +145,11 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   if (int rc = make_map_thd(&tmQ, p->q, p->dtype, p->total_q, p->num_heads_q, p->q_stride_t, p->q_stride_h, 128, "q")) return rc;
   // k/v may legally be empty (total_k == 0): point the maps at q so encoding succeeds; no block is ever loaded.
   const bool kv_empty = p->total_k == 0;
+  const int kv_box_rows = fwd_variant() == 64 ? 64 : 128;
   if (int rc = make_map_thd(&tmK, kv_empty ? p->q : p->k, p->dtype, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
-                            kv_empty ? p->q_stride_t : p->k_stride_t, kv_empty ? p->q_stride_h : p->k_stride_h, 128, "k")) return rc;
+                            kv_empty ? p->q_stride_t : p->k_stride_t, kv_empty ? p->q_stride_h : p->k_stride_h, kv_box_rows, "k")) return rc;
   if (int rc = make_map_thd(&tmV, kv_empty ? p->q : p->v, p->dtype, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
-                            kv_empty ? p->q_stride_t : p->v_stride_t, kv_empty ? p->q_stride_h : p->v_stride_h, 128, "v")) return rc;
+                            kv_empty ? p->q_stride_t : p->v_stride_t, kv_empty ? p->q_stride_h : p->v_stride_h, kv_box_rows, "v")) return rc;
 
   ffa::FwdArgs a{};
   a.meta = meta;
@@ -152,7 +167,8 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   a.lse_stride_h = p->lse_stride_h;
   a.scale = p->softmax_scale;
   a.accumulate = p->accumulate;
-  e = ffa::launch_fwd(p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream);
+  e = fwd_variant() == 64 ? ffa::launch_fwd64(p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream)
+                          : ffa::launch_fwd(p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream);
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "fwd launch: %s", cudaGetErrorString(e));
   ++g_launches;
   return 0;
