@@ -206,7 +206,13 @@ def main():
         pad = compute_pad_size(S, world, chunk)
         assert pad == 0
         r_ = AttnRanges.from_ranges([[0, S]])
-        key = magi_attn_flex_key(r_, r_, "causal", S, S, H, H, D, pad, dist.group.WORLD, chunk_size=chunk)
+        from magiattention_b200.config import DistAttnConfig, OverlapConfig
+        # more, smaller overlap stages at larger cp: the first KV fetch and the last dKV reduce (the only transfers
+        # that cannot hide behind compute) shrink with the stage size
+        degree = int(os.environ.get("B200_OVERLAP_DEGREE", 2 if world <= 2 else 4))
+        cfg = DistAttnConfig(overlap_config=OverlapConfig(enable=True, degree=degree))
+        workload["overlap_degree"] = degree
+        key = magi_attn_flex_key(r_, r_, "causal", S, S, H, H, D, pad, dist.group.WORLD, dist_attn_config=cfg, chunk_size=chunk)
         mgr = get_runtime_mgr(key)
         pos = mgr.get_position_ids()
 

@@ -146,7 +146,9 @@ B200_API int b200_lse_merge(void* out, float* lse, const void* out2, const float
                    int32_t dim, int32_t out_dtype, int32_t out2_dtype, b200_stream_t stream);
 
 /* dst[dst_ranges[i]] += src[src_ranges[i]] row-span by row-span (fp32 accumulate), row = `row_elems`
- * contiguous elements.  ranges are int32 [n,2] device arrays; spans i have equal length on both sides. */
+ * contiguous elements.  ranges are int32 [n,2] device arrays; spans i have equal length on both sides.
+ * Distinct dst spans must not overlap; entries that share the SAME dst span (several sources reduced into one
+ * destination) must be adjacent in the lists — they are folded in one race-free pass. */
 B200_API int b200_range_reduce_sum(void* dst, int32_t dst_dtype, const void* src, int32_t src_dtype,
                           const int32_t* dst_ranges, const int32_t* src_ranges, int32_t num_ranges,
                           int64_t row_elems, b200_stream_t stream);

@@ -43,18 +43,32 @@ __global__ void lse_merge_kernel(TO* __restrict__ out, float* __restrict__ lse, 
   if (lane == 0) lse[rh] = l;
 }
 
+// Row-span accumulate.  Several entries may target the SAME dst span (an output split of group_reduce that
+// receives partial dK/dV from several ranks); such entries must be ADJACENT in the lists: the first entry of a
+// run owns the span and folds every source of the run in one pass (fp32 accumulate, no read-modify-write race).
 template <typename TD, typename TS>
 __global__ void range_reduce_kernel(TD* __restrict__ dst, const TS* __restrict__ src, const int2* __restrict__ dr,
                                     const int2* __restrict__ sr, int n, int64_t row_elems) {
-  // blockIdx.y = range, blockIdx.x strides over the span's elements
-  int r = blockIdx.y;
+  const int r = blockIdx.y;
   if (r >= n) return;
-  int2 d = dr[r], s = sr[r];
-  int64_t len = int64_t(d.y - d.x) * row_elems;
+  const int2 d = dr[r];
+  if (r > 0) {
+    const int2 p = dr[r - 1];
+    if (p.x == d.x && p.y == d.y) return;  // not the run leader
+  }
+  int run = 1;
+  while (r + run < n) {
+    const int2 nx = dr[r + run];
+    if (nx.x != d.x || nx.y != d.y) break;
+    ++run;
+  }
+  const int64_t len = int64_t(d.y - d.x) * row_elems;
   TD* dp = dst + int64_t(d.x) * row_elems;
-  const TS* sp = src + int64_t(s.x) * row_elems;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += int64_t(gridDim.x) * blockDim.x)
-    dp[i] = from_f<TD>(to_f(dp[i]) + to_f(sp[i]));
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += int64_t(gridDim.x) * blockDim.x) {
+    float acc = to_f(dp[i]);
+    for (int k = 0; k < run; ++k) acc += to_f(src[int64_t(sr[r + k].x) * row_elems + i]);
+    dp[i] = from_f<TD>(acc);
+  }
 }
 
 template <typename F>

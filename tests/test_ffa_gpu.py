@@ -287,3 +287,27 @@ def test_block_sparse_gqa_c5_like():
         if lo > 0:
             qr.append(q); kr.append([edges[0], edges[1]])
     _run_case(qr, kr, [0] * len(qr), 4096, 4096, 8, 1, torch.bfloat16)
+
+
+def test_range_reduce_sum_multi_source():
+    """group_reduce's receive-side kernel: several sources folding into the SAME destination span (cp >= 3) must be
+    race-free and exact in fp32 (regression: independent blocks did read-modify-write on the same rows)."""
+    from magiattention_b200 import _lib
+
+    dev = _dev()
+    torch.manual_seed(13)
+    rows, feat = 4096, 256
+    dst = torch.randn(rows, feat, dtype=torch.float32, device=dev)
+    ref = dst.double().clone()
+    src = torch.randn(6000, feat, dtype=torch.float32, device=dev).to(torch.bfloat16)
+    d_spans, s_spans, spos = [], [], 0
+    for (a, b, nsrc) in ((0, 1000, 3), (1000, 1024, 1), (2048, 4096, 2)):
+        for _ in range(nsrc):
+            d_spans.append([a, b]); s_spans.append([spos, spos + (b - a)])
+            ref[a:b] += src[spos:spos + (b - a)].double()
+            spos += b - a
+    mk = lambda r: torch.tensor(r, dtype=torch.int32, device=dev)
+    for _ in range(3):  # repeat: a race would show up as run-to-run differences
+        out = dst.clone()
+        _lib.range_reduce_sum(out, src, mk(d_spans), mk(s_spans))
+        torch.testing.assert_close(out.double(), ref, atol=1e-5, rtol=1e-6)
