@@ -302,7 +302,7 @@ def main():
     # download are exposed.  Every byte of q,k,v,dout goes H2D and every byte of out,dq,dk,dv comes back, every step.
     e2e = None
     if not a.no_e2e:
-        NCH = 8 if H % 8 == 0 else 1
+        NCH = (8 if world == 1 else 2) if H % 8 == 0 else 1  # fewer, larger chunks under CP (per-call comm overhead)
         Hc = H // NCH
         host_in = [[x[:, c * Hc:(c + 1) * Hc].contiguous().pin_memory() for c in range(NCH)] for x in (hq, hk, hv, hdo)]
         host_out = [[torch.empty(S_local, Hc, D, dtype=torch.bfloat16).pin_memory() for _ in range(NCH)] for _ in range(4)]

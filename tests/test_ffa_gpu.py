@@ -299,7 +299,7 @@ def test_range_reduce_sum_multi_source():
     rows, feat = 4096, 256
     dst = torch.randn(rows, feat, dtype=torch.float32, device=dev)
     ref = dst.double().clone()
-    src = torch.randn(6000, feat, dtype=torch.float32, device=dev).to(torch.bfloat16)
+    src = torch.randn(8192, feat, dtype=torch.float32, device=dev).to(torch.bfloat16)
     d_spans, s_spans, spos = [], [], 0
     for (a, b, nsrc) in ((0, 1000, 3), (1000, 1024, 1), (2048, 4096, 2)):
         for _ in range(nsrc):
