@@ -288,10 +288,18 @@ def main():
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         fl_b = 2.5 * flops_fwd(causal_area(S), H)
         ach = fl_b / ms_b / 1e9
+        traffic = None
+        try:  # DRAM bytes per launch of the same kernel at this size, from a committed one-pass ncu capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_256k.json")))
+            if S == 262144 and H == 32:
+                traffic = tr["ffa_bwd_kernel"]["traffic_bytes"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": "ffa_bwd_kernel (event-bracketed b200_ffa_bwd call: plan + preprocess + main)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained",
-                "traffic": None, "fwd_kernel": {"achieved": flops_fwd(causal_area(S), H) / ms_f / 1e9, "ms": ms_f}, "ms": ms_b}
+                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read+write, profiles/traffic_256k.json)",
+                "fwd_kernel": {"achieved": flops_fwd(causal_area(S), H) / ms_f / 1e9, "ms": ms_f}, "ms": ms_b}
     if rank == 0:
         clocks = sampler.stop()
 

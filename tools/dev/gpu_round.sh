@@ -1,5 +1,6 @@
 #!/bin/bash
-# one GPU-box visit: tests, smoke, bench, ncu launch list, ncu full capture of the two attention kernels
+# one GPU-box visit: tests, smoke, bench, ncu launch list, ncu full capture of the two attention kernels,
+# DRAM traffic of the dominant kernel at the full bench size
 set -x
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -8
@@ -12,4 +13,7 @@ tail -3 gpurun_out/ncu_list.err
 ncu --set full --clock-control none --import-source on -k 'regex:ffa_(fwd|bwd)_kernel' -c 2 -f -o gpurun_out/prof \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --seqlen 32768 > gpurun_out/bench_ncu_full.json 2> gpurun_out/ncu_full.err
 tail -3 gpurun_out/ncu_full.err
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k 'regex:ffa_(fwd|bwd)_kernel' -c 2 \
+    --csv --log-file gpurun_out/traffic_256k.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/bench_ncu_traffic.json 2> gpurun_out/ncu_traffic.err
+tail -3 gpurun_out/ncu_traffic.err
 ls -la gpurun_out

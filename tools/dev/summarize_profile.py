@@ -63,6 +63,33 @@ if os.path.exists(rep):
                 if k in idx:
                     f.write(f"   {k:78s} {r[idx[k]]:>18s} {units[idx[k]]}\n")
 
+# ---- DRAM traffic of the attention kernels at the full bench size (one-pass ncu metrics run)
+t = os.path.join(G, "traffic_256k.csv")
+if os.path.exists(t):
+    rows = list(csv.reader(l for l in open(t) if not l.startswith("==")))
+    if rows:
+        hdr = rows[0]
+        ki, mi, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        out = {}
+        for r in rows[1:]:
+            try:
+                v = float(r[vi].replace(",", ""))
+            except Exception:
+                continue
+            unit = r[ui]
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit)
+            kern = "ffa_bwd_kernel" if "ffa_bwd_kernel" in r[ki] else "ffa_fwd_kernel" if "ffa_fwd_kernel" in r[ki] else r[ki][:40]
+            d = out.setdefault(kern, {})
+            if mult is not None:
+                d[r[mi]] = v * mult
+            else:
+                d[r[mi] + "_" + unit] = v
+        for kern, d in out.items():
+            d["traffic_bytes"] = d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+        out["_how"] = ("ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:ffa_(fwd|bwd)_kernel "
+                       "-c 2 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu   (seq 262144, 32 heads, per launch)")
+        json.dump(out, open(os.path.join(OUT, "traffic_256k.json"), "w"), indent=1)
+
 b = os.path.join(G, "bench_n1.json")
 if os.path.exists(b) and os.path.getsize(b):
     with open(os.path.join(OUT, f"{tag}_bench_n1.json"), "w") as f:
