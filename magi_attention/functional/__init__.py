@@ -1,0 +1,4 @@
+from magiattention_b200.functional import (  # noqa: F401
+    DistAttnFunc, DistAttnRuntime, FlexFlashAttnFunc, _flex_flash_attn_backward, _flex_flash_attn_forward,
+    dispatch_func, dist_attn_func, flex_flash_attn_func, undispatch_func,
+)

@@ -7,8 +7,8 @@
 //  * One CTA owns a 256-row q tile of one head (two 128-row MMA tiles that share every K/V block) and
 //    walks ALL slices touching those rows (tile->slice CSR from ffa_plan.cu).  Rows are therefore
 //    reduced across slices in registers/TMEM: no global locks, no fp32 atomics on O, no LSE-merge pass.
-//  * Warp roles (384 threads): warps 0-3 softmax of tile 0, warps 4-7 softmax of tile 1, warp 8 lane 0
-//    issues every tcgen05.mma, warp 9 lane 0 issues every TMA load.  Softmax thread i owns row i of its
+//  * Warp roles (384 threads): warps 0-3 softmax of tile 0, warps 4-7 softmax of tile 1, warp 8 issues every
+//    tcgen05.mma and warp 9 every TMA load (warp-uniform loops, the async instruction under elect.sync).  Softmax thread i owns row i of its
 //    tile (TMEM lane i): row max / row sum need no shuffles.
 //  * TMEM (512 cols): S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P (16-bit) overwrites the
 //    first 64 columns of its S.  MMA order per kv block:  PV0(prev) S0(cur) PV1(prev) S1(cur)  so the
@@ -18,6 +18,8 @@
 //  * Online softmax in base 2 with lazy rescaling: the reference max only moves when it would grow by
 //    more than 2^8, so the O correction (TMEM load-scale-store) is rare and done by the softmax warps
 //    themselves; it is safe because S(cur) completing implies PV(prev) completed (in-order tensor pipe).
+//    The first half of each row's exponentials runs on the stale reference while the block max is computed;
+//    P is published in two halves so the first four PV k-steps can start early.  Packed FFMA2/FADD2 math.
 //  * Epilogue normalises, optionally LSE-merges into a previous partial (out, lse) — the CP stage merge
 //    the reference does with a separate Triton pass (functional/utils.py:467-558) — and stores rows.
 #include <cuda.h>
@@ -27,10 +29,6 @@
 #include "ffa_args.h"
 #include "ffa_kernels.h"
 #include "sm100.cuh"
-
-#ifndef FFA_FWD_PACKED
-#define FFA_FWD_PACKED 1
-#endif
 
 namespace ffa {
 using namespace sm100;

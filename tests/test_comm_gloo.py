@@ -27,6 +27,7 @@ def _worker(rank, world, port, fn, args):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         fn(rank, world, *args)
+        dist.barrier()  # nobody tears the group down while a peer still has traffic in flight
     finally:
         dist.destroy_process_group()
 

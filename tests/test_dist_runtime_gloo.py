@@ -1,0 +1,86 @@
+"""CPU (gloo, world 2 and 4) test of the WHOLE context-parallel runtime — key / planner / dispatch / DistAttnFunc stage
+loop / group_cast / group_reduce / undispatch / autograd — with the CUDA kernels replaced, inside this test only,
+by the oracle acting as an exact fake kernel with the same accumulator semantics (the reference tests its runtime the
+same way with its SDPA backends, tests/README.md:5-8).  The product itself has no such path."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+
+from mask_configs import mask_configs
+from oracle import ffa_oracle as orc
+from test_comm_gloo import _run
+
+
+def _install_fake_kernels():
+    import magiattention_b200._lib as _lib
+    import magiattention_b200.functional.dist_attn as da
+
+    def _mask(qr, kr, ty, tq, tk):
+        return orc.mask_from_slices(qr.tolist(), kr.tolist(), ty.tolist(), tq, tk)
+
+    def fake_fwd(q, k, v, sink, sink_layout, out, lse, qr, kr, ty, scale, softcap, out_type, **kw):
+        o, l = orc.attn_fwd(q.double(), k.double(), v.double(), _mask(qr, kr, ty, q.shape[0], k.shape[0]), scale)
+        mo, ml = orc.merge_out_lse(out.double(), lse.double(), o, l.double())
+        out.copy_(mo)
+        lse.copy_(ml)
+        return out, None
+
+    def _bwd(do, q, k, v, out, lse, qr, kr, ty, scale):
+        return orc.attn_bwd(do.double(), q.double(), k.double(), v.double(), out.double(), lse.double(),
+                            _mask(qr, kr, ty, q.shape[0], k.shape[0]), scale)
+
+    def fake_bwd(do, q, k, v, sink, sink_layout, out, lse, dq, dk, dv, dsink, qr, kr, ty, scale, softcap, **kw):
+        a, b, c = _bwd(do, q, k, v, out, lse, qr, kr, ty, scale)
+        dq += a.to(dq.dtype); dk += b.to(dk.dtype); dv += c.to(dv.dtype)
+        return dq, dk, dv, None
+
+    def fake_lib_bwd(do, q, k, v, out, lse, dq, dk, dv, qr, kr, ty, scale, softcap=0.0, accumulate_dkv=False, sm_margin=0):
+        a, b, c = _bwd(do, q, k, v, out, lse, qr, kr, ty, scale)
+        dq += a.to(dq.dtype)
+        dk.copy_(b); dv.copy_(c)
+        return 3
+
+    da._flex_flash_attn_forward = fake_fwd
+    da._flex_flash_attn_backward = fake_bwd
+    _lib.ffa_bwd = fake_lib_bwd
+
+
+def _runtime_body(rank, world, name, degree):
+    from magiattention_b200.api import calc_attn, compute_pad_size, dispatch, magi_attn_flex_key, undispatch
+    from magiattention_b200.common import AttnRanges
+    from magiattention_b200.config import DistAttnConfig, OverlapConfig
+
+    _install_fake_kernels()
+    cfg = next(c for c in mask_configs(4) if c["name"] == name)
+    T, H, HK, D, chunk = cfg["seqlen"], 2, 1, 8, 16
+    pad = compute_pad_size(T, world, chunk)
+    torch.manual_seed(21)
+    q, k, v, do = (torch.randn(T, h, D, dtype=torch.float64) for h in (H, HK, HK, H))
+    for x in (q, k, v, do):
+        dist.broadcast(x, 0)
+    q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
+    key = magi_attn_flex_key(AttnRanges.from_ranges(cfg["q_ranges"]), AttnRanges.from_ranges(cfg["k_ranges"]), cfg["types"], T, T,
+                             H, HK, D, pad, dist.group.WORLD,
+                             dist_attn_config=DistAttnConfig(overlap_config=OverlapConfig(True, degree)), chunk_size=chunk)
+    ol, meta = calc_attn(dispatch(q, key), dispatch(k, key), dispatch(v, key), key)
+    out = undispatch(ol, key)
+    out.backward(do)
+    mask = orc.mask_from_slices(cfg["q_ranges"], cfg["k_ranges"], cfg["types"], T, T)
+    ro, rl = orc.attn_fwd(q.detach(), k.detach(), v.detach(), mask)
+    rdq, rdk, rdv = orc.attn_bwd(do, q.detach(), k.detach(), v.detach(), ro, rl, mask)
+    torch.testing.assert_close(out.detach(), ro, atol=1e-5, rtol=1e-5)  # fp32 stage accumulators
+    lse_g = undispatch(meta.lse, key)
+    fin = ~torch.isinf(rl)
+    assert torch.equal(torch.isinf(lse_g), ~fin)
+    torch.testing.assert_close(lse_g[fin].double(), rl[fin].double(), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(q.grad, rdq, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(k.grad, rdk, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(v.grad, rdv, atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("world,degree", [(2, 1), (4, 2), (4, 3)])
+@pytest.mark.parametrize("name", ["causal", "sliding_window_causal", "sparse_attn_2k"])
+def test_cp_runtime_end_to_end_gloo(world, degree, name):
+    _run(world, _runtime_body, name, degree)
