@@ -28,8 +28,15 @@ def _worker(rank, world, port, fn, args):
     try:
         fn(rank, world, *args)
         dist.barrier()  # nobody tears the group down while a peer still has traffic in flight
-    finally:
+    except BaseException:
         dist.destroy_process_group()
+        raise
+    dist.destroy_process_group()
+    # skip interpreter teardown: gloo worker threads occasionally abort ("terminate called without an active
+    # exception") when the autograd thread's last work handles are collected after the group is gone
+    import sys
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0)
 
 
 def _run(world, fn, *args):
