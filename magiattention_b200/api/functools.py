@@ -52,6 +52,8 @@ def infer_attn_mask_from_sliding_window(q_range: AttnRange, k_range: AttnRange, 
     planner's exact band decomposition yields CAUSAL / BICAUSAL|FULL / INVCAUSAL pieces."""
     wl, wr = window_size
     q0, q1, k0, k1 = q_range.start, q_range.end, k_range.start, k_range.end
+    if q1 - q0 > k1 - k0:
+        q0 = q1 - (k1 - k0)  # rows above the bottom-right aligned square see no key (reference :209-214)
     sq, sk = q1 - q0, k1 - k0
     if wl < 0 or wl >= sk - 1:
         wl = -1

@@ -173,3 +173,38 @@ def test_planner_block_sparse_many_slices():
     # zero-redundancy: nobody fetches more remote rows than exist outside its shard
     for r in range(cp):
         assert sum(comm[r].num_remote_kv_tokens_per_stage) <= T - dm.shard_seqlen
+
+
+def test_sliding_window_inference_bruteforce():
+    """infer_attn_mask_from_sliding_window vs a brute-force band mask (flash-attn convention, bottom-right aligned),
+    for random q/k spans and windows incl. unbounded sides (-1) — the cases of the reference's
+    tests/test_api/test_functools.py (known answers there are slice lists; here the dense masks must agree)."""
+    from magiattention_b200.api import infer_attn_mask_from_sliding_window
+    from magiattention_b200.common import AttnRange
+
+    g = torch.Generator().manual_seed(5)
+    ri = lambda lo, hi: int(torch.randint(lo, hi, (1,), generator=g))
+    for _ in range(200):
+        q0, sq, k0, sk = ri(0, 10), ri(1, 40), ri(0, 10), ri(1, 40)
+        wl = ri(-1, 45)
+        wr = ri(-1, 45)
+        qr, kr, ty = infer_attn_mask_from_sliding_window(AttnRange(q0, q0 + sq), AttnRange(k0, k0 + sk), (wl, wr))
+        N = 64
+        got = orc.mask_from_slices(qr.to_naive_ranges(), kr.to_naive_ranges(), [t.to_int_type() for t in ty], N, N)
+        i = torch.arange(sq).unsqueeze(1); j = torch.arange(sk).unsqueeze(0)
+        d = sk - sq
+        band = torch.ones(sq, sk, dtype=torch.bool)
+        if wl >= 0:
+            band &= j >= i + d - wl
+        if wr >= 0:
+            band &= j <= i + d + wr
+        if sq > sk:
+            band &= i >= sq - sk  # reference semantics: rows above the bottom-right aligned square are dropped
+        want = torch.zeros(N, N, dtype=torch.bool)
+        want[q0:q0 + sq, k0:k0 + sk] = band
+        assert torch.equal(got, want), (q0, sq, k0, sk, wl, wr)
+        # slices are area-disjoint
+        cover = torch.zeros(N, N, dtype=torch.int32)
+        for (a, b), (c, e) in zip(qr.to_naive_ranges(), kr.to_naive_ranges()):
+            cover[a:b, c:e] += 1
+        assert int(cover.max()) <= 1
