@@ -44,14 +44,14 @@ EncodeTiled_t get_encode() {
   return fn;
 }
 
-// [tokens, heads, 128] 16-bit tensor -> 3-D map (d, h, t), box (64, 1, box_rows), SWIZZLE_128B.
-int make_map_thd(CUtensorMap* m, const void* ptr, int dtype, int tokens, int heads, int64_t stride_t, int64_t stride_h,
+// [tokens, heads, head_dim] 16-bit tensor -> 3-D map (d, h, t), box (64, 1, box_rows), SWIZZLE_128B.
+int make_map_thd(CUtensorMap* m, const void* ptr, int dtype, int head_dim, int tokens, int heads, int64_t stride_t, int64_t stride_h,
                  int box_rows, const char* what) {
   EncodeTiled_t enc = get_encode();
   if (!enc) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (stride_t * 2) % 16 || (stride_h * 2) % 16)
     return fail(B200_ERR_INVALID, "%s: pointer/strides must be 16-byte aligned", what);
-  cuuint64_t dims[3] = {cuuint64_t(ffa::kHeadDim), cuuint64_t(heads), cuuint64_t(tokens)};
+  cuuint64_t dims[3] = {cuuint64_t(head_dim), cuuint64_t(heads), cuuint64_t(tokens)};
   cuuint64_t strides[2] = {cuuint64_t(stride_h) * 2, cuuint64_t(stride_t) * 2};
   cuuint32_t box[3] = {64, 1, cuuint32_t(box_rows)};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -62,11 +62,11 @@ int make_map_thd(CUtensorMap* m, const void* ptr, int dtype, int tokens, int hea
   return 0;
 }
 
-// fp32 [tokens, heads, 128] accumulator -> 3-D map (d, h, t), box (32, 1, 128), SWIZZLE_128B (TMA reduce-add target)
-int make_map_f32_acc(CUtensorMap* m, void* ptr, int tokens, int heads, int64_t stride_t, int64_t stride_h, const char* what) {
+// fp32 [tokens, heads, head_dim] accumulator -> 3-D map (d, h, t), box (32, 1, 128), SWIZZLE_128B (TMA reduce-add target)
+int make_map_f32_acc(CUtensorMap* m, void* ptr, int head_dim, int tokens, int heads, int64_t stride_t, int64_t stride_h, const char* what) {
   EncodeTiled_t enc = get_encode();
   if (!enc) return fail(B200_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
-  cuuint64_t dims[3] = {cuuint64_t(ffa::kHeadDim), cuuint64_t(heads), cuuint64_t(tokens)};
+  cuuint64_t dims[3] = {cuuint64_t(head_dim), cuuint64_t(heads), cuuint64_t(tokens)};
   cuuint64_t strides[2] = {cuuint64_t(stride_h) * 4, cuuint64_t(stride_t) * 4};
   cuuint32_t box[3] = {32, 1, 128};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -90,7 +90,7 @@ int fwd_variant() {
 
 int check_common(int dtype, int hq, int hk, int d, float softcap) {
   if (dtype != B200_F16 && dtype != B200_BF16) return fail(B200_ERR_INVALID, "dtype must be f16 or bf16");
-  if (d != ffa::kHeadDim) return fail(B200_ERR_UNSUPPORTED, "head_dim %d unsupported (only 128)", d);
+  if (d != 64 && d != 128) return fail(B200_ERR_UNSUPPORTED, "head_dim %d unsupported (only 64 and 128)", d);
   if (hq <= 0 || hk <= 0 || hq % hk) return fail(B200_ERR_INVALID, "num_heads_q %d must be a multiple of num_heads_kv %d", hq, hk);
   if (softcap != 0.f) return fail(B200_ERR_UNSUPPORTED, "softcap is not supported");
   return 0;
@@ -142,13 +142,13 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   ++g_launches;
 
   CUtensorMap tmQ, tmK, tmV;
-  if (int rc = make_map_thd(&tmQ, p->q, p->dtype, p->total_q, p->num_heads_q, p->q_stride_t, p->q_stride_h, 128, "q")) return rc;
+  if (int rc = make_map_thd(&tmQ, p->q, p->dtype, p->head_dim, p->total_q, p->num_heads_q, p->q_stride_t, p->q_stride_h, 128, "q")) return rc;
   // k/v may legally be empty (total_k == 0): point the maps at q so encoding succeeds; no block is ever loaded.
   const bool kv_empty = p->total_k == 0;
-  const int kv_box_rows = fwd_variant() == 64 ? 64 : 128;
-  if (int rc = make_map_thd(&tmK, kv_empty ? p->q : p->k, p->dtype, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
+  const int kv_box_rows = (fwd_variant() == 64 && p->head_dim == 128) ? 64 : 128;
+  if (int rc = make_map_thd(&tmK, kv_empty ? p->q : p->k, p->dtype, p->head_dim, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
                             kv_empty ? p->q_stride_t : p->k_stride_t, kv_empty ? p->q_stride_h : p->k_stride_h, kv_box_rows, "k")) return rc;
-  if (int rc = make_map_thd(&tmV, kv_empty ? p->q : p->v, p->dtype, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
+  if (int rc = make_map_thd(&tmV, kv_empty ? p->q : p->v, p->dtype, p->head_dim, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
                             kv_empty ? p->q_stride_t : p->v_stride_t, kv_empty ? p->q_stride_h : p->v_stride_h, kv_box_rows, "v")) return rc;
 
   ffa::FwdArgs a{};
@@ -167,8 +167,10 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   a.lse_stride_h = p->lse_stride_h;
   a.scale = p->softmax_scale;
   a.accumulate = p->accumulate;
-  e = fwd_variant() == 64 ? ffa::launch_fwd64(p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream)
-                          : ffa::launch_fwd(p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream);
+  // the 64-column experimental variant exists for head_dim 128 only
+  e = (fwd_variant() == 64 && p->head_dim == 128)
+          ? ffa::launch_fwd64(p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream)
+          : ffa::launch_fwd(p->head_dim, p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream);
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "fwd launch: %s", cudaGetErrorString(e));
   ++g_launches;
   return 0;
@@ -229,7 +231,7 @@ int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream_) {
   cudaError_t e = ffa::launch_plan(false, meta, n_tiles, capacity, plan, stream);
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "plan launch: %s", cudaGetErrorString(e));
   ++g_launches;
-  e = ffa::launch_bwd_preprocess(p->dtype == B200_BF16, p->out, p->dout, p->lse, delta, lse2, p->total_q, p->num_heads_q, tq_ld,
+  e = ffa::launch_bwd_preprocess(p->head_dim, p->dtype == B200_BF16, p->out, p->dout, p->lse, delta, lse2, p->total_q, p->num_heads_q, tq_ld,
                                  p->o_stride_t, p->o_stride_h, p->do_stride_t, p->do_stride_h, p->lse_stride_t, p->lse_stride_h,
                                  stream);
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "bwd preprocess launch: %s", cudaGetErrorString(e));
@@ -237,15 +239,15 @@ int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream_) {
 
   CUtensorMap tmQ, tmDO, tmK, tmV, tmDQ;
   const bool q_empty = p->total_q == 0;
-  if (int rc = make_map_thd(&tmQ, q_empty ? p->k : p->q, p->dtype, q_empty ? 1 : p->total_q, q_empty ? p->num_heads_kv : p->num_heads_q,
+  if (int rc = make_map_thd(&tmQ, q_empty ? p->k : p->q, p->dtype, p->head_dim, q_empty ? 1 : p->total_q, q_empty ? p->num_heads_kv : p->num_heads_q,
                             q_empty ? p->k_stride_t : p->q_stride_t, q_empty ? p->k_stride_h : p->q_stride_h, 128, "q")) return rc;
-  if (int rc = make_map_thd(&tmDO, q_empty ? p->k : p->dout, p->dtype, q_empty ? 1 : p->total_q, q_empty ? p->num_heads_kv : p->num_heads_q,
+  if (int rc = make_map_thd(&tmDO, q_empty ? p->k : p->dout, p->dtype, p->head_dim, q_empty ? 1 : p->total_q, q_empty ? p->num_heads_kv : p->num_heads_q,
                             q_empty ? p->k_stride_t : p->do_stride_t, q_empty ? p->k_stride_h : p->do_stride_h, 128, "dout")) return rc;
-  if (int rc = make_map_thd(&tmK, p->k, p->dtype, p->total_k, p->num_heads_kv, p->k_stride_t, p->k_stride_h, 128, "k")) return rc;
-  if (int rc = make_map_thd(&tmV, p->v, p->dtype, p->total_k, p->num_heads_kv, p->v_stride_t, p->v_stride_h, 128, "v")) return rc;
+  if (int rc = make_map_thd(&tmK, p->k, p->dtype, p->head_dim, p->total_k, p->num_heads_kv, p->k_stride_t, p->k_stride_h, 128, "k")) return rc;
+  if (int rc = make_map_thd(&tmV, p->v, p->dtype, p->head_dim, p->total_k, p->num_heads_kv, p->v_stride_t, p->v_stride_h, 128, "v")) return rc;
   if (q_empty) {
     tmDQ = tmK;  // never used: no q block is ever visited
-  } else if (int rc = make_map_f32_acc(&tmDQ, p->dq, p->total_q, p->num_heads_q, p->dq_stride_t, p->dq_stride_h, "dq")) {
+  } else if (int rc = make_map_f32_acc(&tmDQ, p->dq, p->head_dim, p->total_q, p->num_heads_q, p->dq_stride_t, p->dq_stride_h, "dq")) {
     return rc;
   }
 
@@ -271,7 +273,7 @@ int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream_) {
   a.dv_stride_h = p->dv_stride_h;
   a.scale = p->softmax_scale;
   a.accumulate_dkv = p->accumulate_dkv;
-  e = ffa::launch_bwd(p->dtype == B200_BF16, p->dkv_dtype == B200_F32, tmQ, tmDO, tmK, tmV, tmDQ, a, stream);
+  e = ffa::launch_bwd(p->head_dim, p->dtype == B200_BF16, p->dkv_dtype == B200_F32, tmQ, tmDO, tmK, tmV, tmDQ, a, stream);
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "bwd launch: %s", cudaGetErrorString(e));
   ++g_launches;
   return 0;

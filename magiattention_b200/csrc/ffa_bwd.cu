@@ -32,14 +32,20 @@ using namespace sm100;
 
 namespace bwd {
 constexpr int kThreads = 512;
-constexpr uint32_t kTileBytes = 128 * 128 * 2;
-constexpr uint32_t kBoxBytes = kTileBytes / 2;
+constexpr uint32_t kBoxBytes = 128 * 64 * 2;  // one TMA box: 128 rows x 64 columns of 16-bit elements
 // K, V resident; dS^T staging; Q double-buffered; dO single-buffered (its next load is issued as soon as dV
 // retires, ~1.5k clocks before dP needs it); two 16 KB staging buffers for the TMA reduce-add of dQ.
-constexpr uint32_t kSmemK = 0, kSmemV = kTileBytes, kSmemDS = 2 * kTileBytes, kSmemQ = 3 * kTileBytes,
-                   kSmemDO = 5 * kTileBytes, kSmemDQ = 6 * kTileBytes, kSmemLse = 7 * kTileBytes,
-                   kSmemDelta = kSmemLse + 1024, kSmemBar = kSmemDelta + 1024, kSmemBytes = kSmemBar + 256;
-constexpr uint32_t kDQChunkBytes = 128 * 32 * 4;
+constexpr uint32_t kDSBytes = 2 * kBoxBytes;      // dS^T staging: 128 kv rows x 128 q columns
+constexpr uint32_t kDQChunkBytes = 128 * 32 * 4;  // one dQ staging chunk: 128 q rows x 32 fp32 columns
+template <int kD> struct Cfg {
+  static_assert(kD == 64 || kD == 128, "head_dim must be 64 or 128");
+  static constexpr uint32_t kBoxes = kD / 64;
+  static constexpr uint32_t kTileBytes = kBoxes * kBoxBytes;  // K, V, Q, dO tiles: 128 rows x kD
+  static constexpr uint32_t kSmemK = 0, kSmemV = kTileBytes, kSmemDS = 2 * kTileBytes, kSmemQ = kSmemDS + kDSBytes,
+                            kSmemDO = kSmemQ + 2 * kTileBytes, kSmemDQ = kSmemDO + kTileBytes,
+                            kSmemLse = kSmemDQ + 2 * kDQChunkBytes, kSmemDelta = kSmemLse + 1024,
+                            kSmemBar = kSmemDelta + 1024, kSmemBytes = kSmemBar + 256;
+};
 constexpr int kBarKV = 0, kBarQFull = 1, kBarQEmpty = 3, kBarDOFull = 5, kBarDOEmpty = 6, kBarS = 9, kBarDP = 10,
               kBarP = 11, kBarDS = 12, kBarDQ = 13, kBarDrained = 14, kBarDKV = 15, kNumBars = 16;
 constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 384;
@@ -48,7 +54,7 @@ constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 384;
 // -------------------------------------------------------------------------------------------------
 // preprocess: delta[h][r] = sum_d O[r,h,d]*dO[r,h,d];  lse2[h][r] = lse[r,h]*log2(e)  (+inf when dead/pad)
 // -------------------------------------------------------------------------------------------------
-template <bool kBF16>
+template <int kD, bool kBF16>
 __global__ void ffa_bwd_preprocess_kernel(const void* __restrict__ out, const void* __restrict__ dout,
                                           const float* __restrict__ lse, float* __restrict__ delta,
                                           float* __restrict__ lse2, int total_q, int num_heads, int tq_ld,
@@ -70,12 +76,18 @@ __global__ void ffa_bwd_preprocess_kernel(const void* __restrict__ out, const vo
   using T = typename std::conditional<kBF16, __nv_bfloat16, __half>::type;
   const T* o = reinterpret_cast<const T*>(out) + int64_t(r) * o_stride_t + int64_t(h) * o_stride_h;
   const T* d = reinterpret_cast<const T*>(dout) + int64_t(r) * do_stride_t + int64_t(h) * do_stride_h;
-  uint2 ov = *reinterpret_cast<const uint2*>(o + lane * 4);
-  uint2 dv = *reinterpret_cast<const uint2*>(d + lane * 4);
+  constexpr int kWords = kD / 64;  // 32-bit words (element pairs) per lane
+  uint32_t ow[kWords], dw[kWords];
+  if constexpr (kD == 128) {
+    const uint2 ov = *reinterpret_cast<const uint2*>(o + lane * 4), dv = *reinterpret_cast<const uint2*>(d + lane * 4);
+    ow[0] = ov.x; ow[1] = ov.y; dw[0] = dv.x; dw[1] = dv.y;
+  } else {
+    ow[0] = *reinterpret_cast<const uint32_t*>(o + lane * 2);
+    dw[0] = *reinterpret_cast<const uint32_t*>(d + lane * 2);
+  }
   float acc = 0.f;
-  const uint32_t ow[2] = {ov.x, ov.y}, dw[2] = {dv.x, dv.y};
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kWords; ++i) {
     float o0, o1, d0, d1;
     if constexpr (kBF16) {
       o0 = __uint_as_float(ow[i] << 16); o1 = __uint_as_float(ow[i] & 0xffff0000u);
@@ -123,12 +135,17 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                : "memory");
 }
 
-template <bool kBF16, bool kDkvF32>
+template <int kD, bool kBF16, bool kDkvF32>
 __global__ void __launch_bounds__(bwd::kThreads, 1)
 ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                const __grid_constant__ CUtensorMap tmDQ, const BwdArgs args) {
   using namespace bwd;
+  using C = Cfg<kD>;
+  constexpr uint32_t kTileBytes = C::kTileBytes, kBoxes = C::kBoxes;
+  constexpr uint32_t kSmemK = C::kSmemK, kSmemV = C::kSmemV, kSmemDS = C::kSmemDS, kSmemQ = C::kSmemQ, kSmemDO = C::kSmemDO,
+                     kSmemDQ = C::kSmemDQ, kSmemLse = C::kSmemLse, kSmemDelta = C::kSmemDelta, kSmemBar = C::kSmemBar;
+  constexpr int kDh = kD / 2;  // head-dim columns each compute warpgroup writes in the dK/dV epilogue
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemBar + kNumBars * 8);
@@ -285,11 +302,11 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       DT* base = reinterpret_cast<DT*>(which == 0 ? args.dv : args.dk);
       const int64_t st_t = which == 0 ? args.dv_stride_t : args.dk_stride_t;
       const int64_t st_h = which == 0 ? args.dv_stride_h : args.dk_stride_h;
-      DT* rowp = base + int64_t(c) * st_t + int64_t(hk) * st_h + half * 64;
+      DT* rowp = base + int64_t(c) * st_t + int64_t(hk) * st_h + half * kDh;
       const float mul = which == 0 ? 1.f : args.scale;
-      const uint32_t tsrc = tmem + lane_off + (which == 0 ? kTmemDV : kTmemDK) + half * 64;
+      const uint32_t tsrc = tmem + lane_off + (which == 0 ? kTmemDV : kTmemDK) + half * kDh;
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+      for (int ch = 0; ch < kDh / 32; ++ch) {
         float x[32];
         if (it > 0) {
           uint32_t r[32];
@@ -353,12 +370,12 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           // two halves of 64 columns: the TMEM region is released (kBarDrained) as soon as the second half sits
           // in registers, i.e. after staging only the first half
 #pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
+          for (int h2 = 0; h2 < kD / 64; ++h2) {
             uint32_t r[2][32];
             tmem_ld32(tDQ + h2 * 64, r[0]);
             tmem_ld32(tDQ + h2 * 64 + 32, r[1]);
             tc_wait_ld();
-            if (h2 == 1) {
+            if (h2 == kD / 64 - 1) {
               tc_fence_before();
               mbar_arrive(bar(kBarDrained));  // TMEM dQ region may be overwritten by the next dP
             }
@@ -393,9 +410,9 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       {
         // ================================ MMA issuer ================================
         // warp-uniform loop (descriptors stay in uniform registers); one elected lane issues the async ops
-        constexpr uint32_t id_kk = make_idesc(kBF16, false, false, 128, 128);  // S^T, dP^T : both K-major
-        constexpr uint32_t id_tm = make_idesc(kBF16, false, true, 128, 128);   // dV, dK : A tmem, B MN-major
-        constexpr uint32_t id_mm = make_idesc(kBF16, true, true, 128, 128);    // dQ : A, B MN-major
+        constexpr uint32_t id_kk = make_idesc(kBF16, false, false, 128, 128);  // S^T, dP^T [128 kv x 128 q], contraction over kD
+        constexpr uint32_t id_tm = make_idesc(kBF16, false, true, 128, kD);    // dV, dK [128 kv x kD]: A tmem, B MN-major
+        constexpr uint32_t id_mm = make_idesc(kBF16, true, true, 128, kD);     // dQ [128 q x kD]: A, B MN-major
         constexpr uint64_t mn_hi = desc_mnmajor(kBoxBytes);
         const uint32_t sK = smem_base + kSmemK, sV = smem_base + kSmemV, sDS = smem_base + kSmemDS;
         const uint32_t tS = tmem + kTmemS, tDP = tmem + kTmemDP, tDV = tmem + kTmemDV, tDK = tmem + kTmemDK;
@@ -404,7 +421,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         auto mma_kmajor = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t commit_bar) {
           if (elect_one()) {
 #pragma unroll
-            for (uint32_t kk = 0; kk < 8; ++kk) {
+            for (uint32_t kk = 0; kk < kD / 16; ++kk) {  // contraction over the head dim
               const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
               mma_ss(d, smem_desc(DESC_KMAJOR, a + off), smem_desc(DESC_KMAJOR, b + off), id_kk, kk > 0 ? 1u : 0u);
             }
@@ -497,10 +514,11 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (!kv_loaded) {
               if (elect_one()) {
                 mbar_arrive_expect_tx(bar(kBarKV), 2 * kTileBytes);
-                tma_load_3d(smem_base + kSmemK, &tmK, bar(kBarKV), 0, hk, C0);
-                tma_load_3d(smem_base + kSmemK + kBoxBytes, &tmK, bar(kBarKV), 64, hk, C0);
-                tma_load_3d(smem_base + kSmemV, &tmV, bar(kBarKV), 0, hk, C0);
-                tma_load_3d(smem_base + kSmemV + kBoxBytes, &tmV, bar(kBarKV), 64, hk, C0);
+#pragma unroll
+                for (uint32_t bx = 0; bx < kBoxes; ++bx) {
+                  tma_load_3d(smem_base + kSmemK + bx * kBoxBytes, &tmK, bar(kBarKV), 64 * bx, hk, C0);
+                  tma_load_3d(smem_base + kSmemV + bx * kBoxBytes, &tmV, bar(kBarKV), 64 * bx, hk, C0);
+                }
               }
               __syncwarp();
               kv_loaded = true;
@@ -512,8 +530,9 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               if (elect_one()) {
                 mbar_arrive_expect_tx(bar(kBarQFull + st), kTileBytes + 1024);
                 const uint32_t sQ = smem_base + kSmemQ + st * kTileBytes;
-                tma_load_3d(sQ, &tmQ, bar(kBarQFull + st), 0, hq, rs);
-                tma_load_3d(sQ + kBoxBytes, &tmQ, bar(kBarQFull + st), 64, hq, rs);
+#pragma unroll
+                for (uint32_t bx = 0; bx < kBoxes; ++bx)
+                  tma_load_3d(sQ + bx * kBoxBytes, &tmQ, bar(kBarQFull + st), 64 * bx, hq, rs);
                 bulk_load(smem_base + kSmemLse + st * 512, lse2 + rs, 512, bar(kBarQFull + st));
                 bulk_load(smem_base + kSmemDelta + st * 512, delta + rs, 512, bar(kBarQFull + st));
               }
@@ -522,8 +541,9 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               if (elect_one()) {
                 mbar_arrive_expect_tx(bar(kBarDOFull), kTileBytes);
                 const uint32_t sDO = smem_base + kSmemDO;
-                tma_load_3d(sDO, &tmDO, bar(kBarDOFull), 0, hq, rs);
-                tma_load_3d(sDO + kBoxBytes, &tmDO, bar(kBarDOFull), 64, hq, rs);
+#pragma unroll
+                for (uint32_t bx = 0; bx < kBoxes; ++bx)
+                  tma_load_3d(sDO + bx * kBoxBytes, &tmDO, bar(kBarDOFull), 64 * bx, hq, rs);
               }
               __syncwarp();
             }
@@ -540,7 +560,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // -------------------------------------------------------------------------------------------------
 // host launchers
 // -------------------------------------------------------------------------------------------------
-cudaError_t launch_bwd_preprocess(bool bf16, const void* out, const void* dout, const float* lse, float* delta,
+cudaError_t launch_bwd_preprocess(int head_dim, bool bf16, const void* out, const void* dout, const float* lse, float* delta,
                                   float* lse2, int total_q, int num_heads, int tq_ld, int64_t o_stride_t,
                                   int64_t o_stride_h, int64_t do_stride_t, int64_t do_stride_h, int64_t lse_stride_t,
                                   int64_t lse_stride_h, cudaStream_t stream) {
@@ -548,40 +568,51 @@ cudaError_t launch_bwd_preprocess(bool bf16, const void* out, const void* dout, 
   const int wpb = 8;
   const unsigned blocks = unsigned((total + wpb - 1) / wpb);
   if (blocks == 0) return cudaSuccess;
-  if (bf16)
-    ffa_bwd_preprocess_kernel<true><<<blocks, wpb * 32, 0, stream>>>(out, dout, lse, delta, lse2, total_q, num_heads, tq_ld,
-                                                                   o_stride_t, o_stride_h, do_stride_t, do_stride_h,
-                                                                   lse_stride_t, lse_stride_h);
-  else
-    ffa_bwd_preprocess_kernel<false><<<blocks, wpb * 32, 0, stream>>>(out, dout, lse, delta, lse2, total_q, num_heads, tq_ld,
-                                                                    o_stride_t, o_stride_h, do_stride_t, do_stride_h,
-                                                                    lse_stride_t, lse_stride_h);
+#define FFA_PRE(D_, B_)                                                                                                   \
+  ffa_bwd_preprocess_kernel<D_, B_><<<blocks, wpb * 32, 0, stream>>>(out, dout, lse, delta, lse2, total_q, num_heads, tq_ld, \
+                                                                     o_stride_t, o_stride_h, do_stride_t, do_stride_h,      \
+                                                                     lse_stride_t, lse_stride_h)
+  if (head_dim == 64) {
+    if (bf16) FFA_PRE(64, true); else FFA_PRE(64, false);
+  } else {
+    if (bf16) FFA_PRE(128, true); else FFA_PRE(128, false);
+  }
+#undef FFA_PRE
   return cudaGetLastError();
 }
 
-template <bool kBF16, bool kDkvF32>
+template <int kD, bool kBF16, bool kDkvF32>
 static cudaError_t launch_bwd_one(const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK,
                                   const CUtensorMap& tmV, const CUtensorMap& tmDQ, const BwdArgs& a, int grid,
                                   cudaStream_t stream) {
-  auto kern = ffa_bwd_kernel<kBF16, kDkvF32>;
+  auto kern = ffa_bwd_kernel<kD, kBF16, kDkvF32>;
+  constexpr uint32_t smem_bytes = bwd::Cfg<kD>::kSmemBytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, bwd::kThreads, bwd::kSmemBytes, stream>>>(tmQ, tmDO, tmK, tmV, tmDQ, a);
+  kern<<<grid, bwd::kThreads, smem_bytes, stream>>>(tmQ, tmDO, tmK, tmV, tmDQ, a);
   return cudaGetLastError();
 }
 
-cudaError_t launch_bwd(bool bf16, bool dkv_f32, const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK,
-                       const CUtensorMap& tmV, const CUtensorMap& tmDQ, const BwdArgs& a, cudaStream_t stream) {
+template <int kD>
+static cudaError_t launch_bwd_d(bool bf16, bool dkv_f32, const CUtensorMap& tmQ, const CUtensorMap& tmDO, const CUtensorMap& tmK,
+                                const CUtensorMap& tmV, const CUtensorMap& tmDQ, const BwdArgs& a, int grid, cudaStream_t stream) {
+  if (bf16) return dkv_f32 ? launch_bwd_one<kD, true, true>(tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream)
+                           : launch_bwd_one<kD, true, false>(tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream);
+  return dkv_f32 ? launch_bwd_one<kD, false, true>(tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream)
+                 : launch_bwd_one<kD, false, false>(tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream);
+}
+
+cudaError_t launch_bwd(int head_dim, bool bf16, bool dkv_f32, const CUtensorMap& tmQ, const CUtensorMap& tmDO,
+                       const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmDQ, const BwdArgs& a,
+                       cudaStream_t stream) {
   const int grid = a.n_tiles * a.num_heads_kv;
   if (grid == 0) return cudaSuccess;
-  if (bf16) return dkv_f32 ? launch_bwd_one<true, true>(tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream)
-                           : launch_bwd_one<true, false>(tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream);
-  return dkv_f32 ? launch_bwd_one<false, true>(tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream)
-                 : launch_bwd_one<false, false>(tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream);
+  return head_dim == 64 ? launch_bwd_d<64>(bf16, dkv_f32, tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream)
+                        : launch_bwd_d<128>(bf16, dkv_f32, tmQ, tmDO, tmK, tmV, tmDQ, a, grid, stream);
 }
 
 }  // namespace ffa

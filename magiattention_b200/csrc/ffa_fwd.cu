@@ -36,12 +36,17 @@ using namespace sm100;
 namespace fwd {
 constexpr int kThreads = 384;
 constexpr int kStages = 5;
-constexpr uint32_t kTileBytes = 128 * 128 * 2;  // one 128x128 16-bit operand tile (2 boxes)
-constexpr uint32_t kBoxBytes = kTileBytes / 2;
-constexpr uint32_t kSmemQ = 0;
-constexpr uint32_t kSmemKV = 2 * kTileBytes;
-constexpr uint32_t kSmemBar = kSmemKV + kStages * kTileBytes;
-constexpr uint32_t kSmemBytes = kSmemBar + 256;
+constexpr uint32_t kBoxBytes = 128 * 64 * 2;  // one TMA box: 128 rows x 64 columns of 16-bit elements
+// operand tiles are 128 rows x kD columns = kD/64 boxes; smem map: [Q0 Q1][K/V ring of kStages tiles][barriers]
+template <int kD> struct Cfg {
+  static_assert(kD == 64 || kD == 128, "head_dim must be 64 or 128");
+  static constexpr uint32_t kBoxes = kD / 64;
+  static constexpr uint32_t kTileBytes = kBoxes * kBoxBytes;
+  static constexpr uint32_t kSmemQ = 0;
+  static constexpr uint32_t kSmemKV = 2 * kTileBytes;
+  static constexpr uint32_t kSmemBar = kSmemKV + kStages * kTileBytes;
+  static constexpr uint32_t kSmemBytes = kSmemBar + 256;
+};
 // barrier indices
 constexpr int kBarQ = 0, kBarFull = 1, kBarEmpty = kBarFull + kStages, kBarS = kBarEmpty + kStages, kBarP = kBarS + 2,
               kBarPhi = kBarP + 2, kBarO = kBarPhi + 2, kNumBars = kBarO + 2;  // kBarP: first half of P, kBarPhi: second
@@ -117,11 +122,13 @@ __device__ __forceinline__ float2 softmax_half(const uint32_t* sr, float sl2, fl
   return __fadd2_rn(a01, a23);
 }
 
-template <bool kBF16, bool kOutF32>
+template <int kD, bool kBF16, bool kOutF32>
 __global__ void __launch_bounds__(fwd::kThreads, 1)
 ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const FwdArgs args) {
   using namespace fwd;
+  constexpr uint32_t kTileBytes = Cfg<kD>::kTileBytes, kBoxes = Cfg<kD>::kBoxes;
+  constexpr uint32_t kSmemQ = Cfg<kD>::kSmemQ, kSmemKV = Cfg<kD>::kSmemKV, kSmemBar = Cfg<kD>::kSmemBar;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemBar + kNumBars * 8);
@@ -248,7 +255,7 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           if (n_act > 0) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < kD / 32; ++c) {
               uint32_t o[32];
               tmem_ld32(tO + c * 32, o);
               tc_wait_ld();
@@ -304,7 +311,7 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     OutT* orow = reinterpret_cast<OutT*>(args.out) + int64_t(row) * args.o_stride_t + int64_t(hq) * args.o_stride_h;
     const bool skip_store = !row_ok || (args.accumulate && dead && need_old);  // nothing new: keep the old partial
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < kD / 32; ++c) {
       float o[32];
       if (n_act > 0) {
         uint32_t r[32];
@@ -377,7 +384,7 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // The whole warp runs this loop with warp-uniform control flow (descriptors live in uniform registers);
       // only the tcgen05.mma / tcgen05.commit instructions themselves are issued by one elected lane.
       constexpr uint32_t idesc_s = make_idesc(kBF16, false, false, 128, 128);
-      constexpr uint32_t idesc_pv = make_idesc(kBF16, false, true, 128, 128);
+      constexpr uint32_t idesc_pv = make_idesc(kBF16, false, true, 128, kD);  // O tile is 128 x kD
       constexpr uint64_t desc_v_hi = desc_mnmajor(kBoxBytes);
       const uint32_t sQ = smem_base + kSmemQ, sKV = smem_base + kSmemKV;
       uint32_t n_act0 = 0, n_act1 = 0;            // active blocks issued so far per tile
@@ -416,7 +423,7 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t tSt = tmem + kTmemS + t * 128;
         if (elect_one()) {
 #pragma unroll
-          for (uint32_t kk = 0; kk < 8; ++kk) {
+          for (uint32_t kk = 0; kk < kD / 16; ++kk) {  // contraction over the head dim
             const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
             mma_ss(tSt, smem_desc(DESC_KMAJOR, sQ + t * kTileBytes + off), smem_desc(DESC_KMAJOR, sK + off), idesc_s,
                    kk > 0 ? 1u : 0u);
@@ -481,8 +488,9 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_arrive_expect_tx(bar(kBarQ), 2 * kTileBytes);
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-              tma_load_3d(sQ + t * kTileBytes, &tmQ, bar(kBarQ), 0, hq, R0 + t * kBlockM);
-              tma_load_3d(sQ + t * kTileBytes + kBoxBytes, &tmQ, bar(kBarQ), 64, hq, R0 + t * kBlockM);
+#pragma unroll
+              for (uint32_t bx = 0; bx < kBoxes; ++bx)
+                tma_load_3d(sQ + t * kTileBytes + bx * kBoxBytes, &tmQ, bar(kBarQ), 64 * bx, hq, R0 + t * kBlockM);
             }
           }
           __syncwarp();
@@ -497,8 +505,9 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (elect_one()) {
               mbar_arrive_expect_tx(bar(kBarFull + buf), kTileBytes);
               const CUtensorMap* tm = which == 0 ? &tmK : &tmV;
-              tma_load_3d(sKV + buf * kTileBytes, tm, bar(kBarFull + buf), 0, hk, bs);
-              tma_load_3d(sKV + buf * kTileBytes + kBoxBytes, tm, bar(kBarFull + buf), 64, hk, bs);
+#pragma unroll
+              for (uint32_t bx = 0; bx < kBoxes; ++bx)
+                tma_load_3d(sKV + buf * kTileBytes + bx * kBoxBytes, tm, bar(kBarFull + buf), 64 * bx, hk, bs);
             }
             __syncwarp();
           }
@@ -514,28 +523,36 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------
-template <bool kBF16, bool kOutF32>
+template <int kD, bool kBF16, bool kOutF32>
 static cudaError_t launch_one(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                               const FwdArgs& a, int grid, cudaStream_t stream) {
-  auto kern = ffa_fwd_kernel<kBF16, kOutF32>;
+  auto kern = ffa_fwd_kernel<kD, kBF16, kOutF32>;
+  constexpr uint32_t smem_bytes = fwd::Cfg<kD>::kSmemBytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, fwd::kThreads, fwd::kSmemBytes, stream>>>(tmQ, tmK, tmV, a);
+  kern<<<grid, fwd::kThreads, smem_bytes, stream>>>(tmQ, tmK, tmV, a);
   return cudaGetLastError();
 }
 
-cudaError_t launch_fwd(bool bf16, bool out_f32, const CUtensorMap& tmQ, const CUtensorMap& tmK,
+template <int kD>
+static cudaError_t launch_d(bool bf16, bool out_f32, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                            const FwdArgs& a, int grid, cudaStream_t stream) {
+  if (bf16) return out_f32 ? launch_one<kD, true, true>(tmQ, tmK, tmV, a, grid, stream)
+                           : launch_one<kD, true, false>(tmQ, tmK, tmV, a, grid, stream);
+  return out_f32 ? launch_one<kD, false, true>(tmQ, tmK, tmV, a, grid, stream)
+                 : launch_one<kD, false, false>(tmQ, tmK, tmV, a, grid, stream);
+}
+
+cudaError_t launch_fwd(int head_dim, bool bf16, bool out_f32, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                        const CUtensorMap& tmV, const FwdArgs& a, cudaStream_t stream) {
   const int grid = a.n_tiles * a.num_heads_q;
   if (grid == 0) return cudaSuccess;
-  if (bf16) return out_f32 ? launch_one<true, true>(tmQ, tmK, tmV, a, grid, stream)
-                           : launch_one<true, false>(tmQ, tmK, tmV, a, grid, stream);
-  return out_f32 ? launch_one<false, true>(tmQ, tmK, tmV, a, grid, stream)
-                 : launch_one<false, false>(tmQ, tmK, tmV, a, grid, stream);
+  return head_dim == 64 ? launch_d<64>(bf16, out_f32, tmQ, tmK, tmV, a, grid, stream)
+                        : launch_d<128>(bf16, out_f32, tmQ, tmK, tmV, a, grid, stream);
 }
 
 }  // namespace ffa

@@ -94,7 +94,7 @@ def test_argument_validation_needs_no_gpu(lib):
     from magiattention_b200 import _lib
 
     p = _lib.FwdParams()
-    p.dtype, p.head_dim, p.num_heads_q, p.num_heads_kv = _lib.B200_BF16, 64, 2, 2
+    p.dtype, p.head_dim, p.num_heads_q, p.num_heads_kv = _lib.B200_BF16, 96, 2, 2
     assert lib.b200_ffa_fwd(C.byref(p), None) == -4  # B200_ERR_UNSUPPORTED
     assert b"head_dim" in lib.b200_ffa_last_error()
     p.head_dim, p.num_heads_kv = 128, 3

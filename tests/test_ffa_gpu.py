@@ -24,7 +24,7 @@ def _dev():
     return torch.device("cuda:0")
 
 
-def _run_case(qr, kr, ty, T, TK, HQ, HK, dtype, seed=0, check_bwd=True):
+def _run_case(qr, kr, ty, T, TK, HQ, HK, dtype, seed=0, check_bwd=True, D=D):
     from magiattention_b200.functional import flex_flash_attn_func
 
     dev = _dev()
@@ -66,6 +66,24 @@ def test_ffa_mask_configs(cfg, dtype):
 @pytest.mark.parametrize("hq,hk", [(1, 1), (4, 4), (8, 2)])
 def test_ffa_head_configs(hq, hk):
     _run_case([[0, 700]], [[0, 900]], [1], 700, 900, hq, hk, torch.bfloat16)
+
+
+_HD64_CASES = ("varlen_causal_1k", "all_types_aspects", "sliding_window_causal", "uncovered_rows")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_ffa_head_dim_64(dtype):
+    """head_dim 64 (Llama-3-1B geometry of examples/torch_native): every mask type, GQA 4:1, ragged sizes, fwd + bwd."""
+    cfgs = mask_configs(1)
+    picked = [c for c in cfgs if c["name"] in _HD64_CASES]
+    assert len(picked) == len(_HD64_CASES)
+    for cfg in picked:
+        T = cfg["seqlen"]
+        _run_case(cfg["q_ranges"], cfg["k_ranges"], cfg["types"], T, T, 4, 1, dtype, D=64)
+    _run_case([[0, 77], [77, 77], [100, 333], [333, 600]], [[0, 50], [3, 9], [10, 50], [20, 450]], [0, 0, 2, 3], 600, 450, 2, 2,
+              dtype, D=64)
+    _run_case([[0, 700]], [[0, 900]], [1], 700, 900, 8, 2, dtype, D=64)
+    _run_case([], [], [], 130, 70, 2, 1, dtype, D=64)
 
 
 def test_ffa_ragged_and_empty():
@@ -165,8 +183,8 @@ def test_error_behaviour():
     with pytest.raises(AssertionError):
         flex_flash_attn_func(q, q, q, r, r, None, sink=torch.zeros(1, 2, device=dev))
     with pytest.raises(RuntimeError):
-        q64 = torch.randn(64, 2, 64, dtype=torch.bfloat16, device=dev)
-        flex_flash_attn_func(q64, q64, q64, r, r, None)
+        q96 = torch.randn(64, 2, 96, dtype=torch.bfloat16, device=dev)
+        flex_flash_attn_func(q96, q96, q96, r, r, None)
     with pytest.raises(RuntimeError):
         flex_flash_attn_func(q.cpu(), q.cpu(), q.cpu(), r.cpu(), r.cpu(), None)
 

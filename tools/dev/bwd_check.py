@@ -91,7 +91,7 @@ def stage_C():
     import torch
     from magiattention_b200 import _lib
     dev = torch.device("cuda:0")
-    D = 128
+    D = int(os.environ.get("FFA_CHECK_D", "128"))
     for name, T, H, ty in (("causal 4K h16", 4096, 16, 1), ("causal 16K h16", 16384, 16, 1),
                            ("full 8K h16", 8192, 16, 0), ("causal 32K h8", 32768, 8, 1)):
         q, k, v, do = (torch.randn(T, H, D, dtype=torch.bfloat16, device=dev) for _ in range(4))
