@@ -54,7 +54,7 @@ enum b200_status {
   B200_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
   B200_ERR_WORKSPACE = -2,   /* workspace too small or misaligned */
   B200_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed */
-  B200_ERR_UNSUPPORTED = -4  /* valid in the reference, not implemented here (e.g. sink, softcap) */
+  B200_ERR_UNSUPPORTED = -4  /* valid in the reference, not implemented here (e.g. softcap) */
 };
 
 typedef struct {
@@ -89,6 +89,18 @@ typedef struct {
   int32_t sm_margin;           /* SMs to leave free for concurrent comm kernels */
   void* workspace;             /* >= b200_ffa_fwd_workspace_bytes(), 256-byte aligned */
   size_t workspace_bytes;
+  /* attention sink (NULL = none): `seqlen_sink` (<= 8, like the reference's kMaxSeqlenSink,
+   * flash_fwd_postprocess_kernel.h:88) extra fp32 logit columns with zero value vectors, merged into (out, lse)
+   * AFTER the slices: lse' = logaddexp(lse, logsumexp(sink)), out' = out * exp(lse - lse').  A CP runtime passes
+   * the sink on exactly one stage (reference: host stage only, dist_attn.py:1278-1280).
+   * sink_layout 0 = "sh" [seqlen_sink, num_heads_q], 1 = "ssh" [total_q, seqlen_sink, num_heads_q]. */
+  const float* sink;
+  int32_t seqlen_sink;
+  int32_t sink_layout;
+  /* max_logits (NULL = not wanted): fp32 [num_heads_q]; max-reduced IN PLACE with the largest scaled logit
+   * softmax_scale * q.k over every unmasked pair of this call (reference: return_max_logits,
+   * flex_flash_attn.py:397-403; initialise to -inf for a fresh result). */
+  float* max_logits;
 } b200_ffa_fwd_params;
 
 typedef struct {
@@ -126,6 +138,13 @@ typedef struct {
   int32_t sm_margin;
   void* workspace;
   size_t workspace_bytes;
+  /* attention sink gradient (sink NULL = none): dsink (fp32, same layout as sink) is ACCUMULATED into:
+   * dsink_j -= sum_rows exp(sink_j - lse_row) * rowsum(out o dout)_row, with `lse` the global lse that includes the
+   * sink (reference: sink_bwd, functional/utils.py:117-206).  Zero it first for a fresh result. */
+  const float* sink;
+  float* dsink;
+  int32_t seqlen_sink;
+  int32_t sink_layout;
 } b200_ffa_bwd_params;
 
 /* Library / build identification: "b200_ffa <version> sm_100a". */

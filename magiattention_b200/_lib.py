@@ -38,6 +38,8 @@ class FwdParams(C.Structure):
         ("dtype", C.c_int32), ("out_dtype", C.c_int32),
         ("accumulate", C.c_int32), ("sm_margin", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("sink", C.c_void_p), ("seqlen_sink", C.c_int32), ("sink_layout", C.c_int32),
+        ("max_logits", C.c_void_p),
     ]
 
 
@@ -63,6 +65,7 @@ class BwdParams(C.Structure):
         ("dtype", C.c_int32), ("dkv_dtype", C.c_int32),
         ("accumulate_dkv", C.c_int32), ("sm_margin", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("sink", C.c_void_p), ("dsink", C.c_void_p), ("seqlen_sink", C.c_int32), ("sink_layout", C.c_int32),
     ]
 
 
@@ -145,11 +148,31 @@ def _ranges_ptr(r: torch.Tensor | None, n: int, name: str) -> int:
     return r.data_ptr()
 
 
+SINK_LAYOUTS = {"sh": 0, "ssh": 1}
+
+
+def _sink_args(sink: torch.Tensor | None, sink_layout: str, total_q: int, heads: int, device) -> tuple[int, int, int]:
+    """(pointer, seqlen_sink, layout code) of a sink tensor: fp32, "sh" [s_sink, hq] or "ssh" [tq, s_sink, hq]."""
+    if sink is None:
+        return 0, 0, 0
+    if sink_layout == "shd":
+        raise NotImplementedError(f"sink_layout {sink_layout} is not supported yet")
+    if sink_layout not in SINK_LAYOUTS:
+        raise ValueError(f"Invalid sink_layout {sink_layout}")
+    if sink.dtype != torch.float32 or not sink.is_cuda or not sink.is_contiguous() or sink.device != device:
+        raise RuntimeError("sink must be a contiguous fp32 CUDA tensor on q's device")
+    want = (sink.shape[0], heads) if sink_layout == "sh" else (total_q, sink.shape[1] if sink.dim() == 3 else -1, heads)
+    if tuple(sink.shape) != want:
+        raise RuntimeError(f"sink with layout {sink_layout!r} must have shape {want}, got {tuple(sink.shape)}")
+    return sink.data_ptr(), int(sink.shape[0] if sink_layout == "sh" else sink.shape[1]), SINK_LAYOUTS[sink_layout]
+
+
 def ffa_fwd(
     q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
     out: torch.Tensor, lse: torch.Tensor,
     q_ranges: torch.Tensor, k_ranges: torch.Tensor, attn_type_map: torch.Tensor | None,
     softmax_scale: float, softcap: float = 0.0, accumulate: bool = False, sm_margin: int = 0,
+    sink: torch.Tensor | None = None, sink_layout: str = "sh", max_logits: torch.Tensor | None = None,
 ) -> int:
     """Enqueue the forward on the current stream; returns the number of kernels launched."""
     l = lib()
@@ -175,6 +198,12 @@ def ffa_fwd(
     p.softmax_scale, p.softcap = softmax_scale, softcap
     p.dtype, p.out_dtype = _DT[q.dtype], _DT[out.dtype]
     p.accumulate, p.sm_margin = int(accumulate), sm_margin
+    p.sink, p.seqlen_sink, p.sink_layout = _sink_args(sink, sink_layout, q.shape[0], q.shape[1], q.device)
+    if max_logits is not None:
+        if max_logits.dtype != torch.float32 or tuple(max_logits.shape) != (q.shape[1],) or not max_logits.is_contiguous() \
+                or max_logits.device != q.device:
+            raise RuntimeError("max_logits must be a contiguous fp32 [num_heads_q] tensor on q's device")
+        p.max_logits = max_logits.data_ptr()
     nbytes = l.b200_ffa_fwd_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, q.device)
     p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
@@ -187,8 +216,9 @@ def ffa_bwd(
     dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor,
     q_ranges: torch.Tensor, k_ranges: torch.Tensor, attn_type_map: torch.Tensor | None,
     softmax_scale: float, softcap: float = 0.0, accumulate_dkv: bool = False, sm_margin: int = 0,
+    sink: torch.Tensor | None = None, sink_layout: str = "sh", dsink: torch.Tensor | None = None,
 ) -> int:
-    """Enqueue the backward on the current stream (dq fp32 is accumulated into)."""
+    """Enqueue the backward on the current stream (dq fp32 — and dsink when a sink is given — are accumulated into)."""
     l = lib()
     for t, n in ((dout, "dout"), (q, "q"), (k, "k"), (v, "v"), (out, "out"), (dq, "dq"), (dk, "dk"), (dv, "dv")):
         _req(t, n)
@@ -214,6 +244,12 @@ def ffa_bwd(
     p.softmax_scale, p.softcap = softmax_scale, softcap
     p.dtype, p.dkv_dtype = _DT[q.dtype], _DT[dk.dtype]
     p.accumulate_dkv, p.sm_margin = int(accumulate_dkv), sm_margin
+    p.sink, p.seqlen_sink, p.sink_layout = _sink_args(sink, sink_layout, q.shape[0], q.shape[1], q.device)
+    if sink is not None:
+        if dsink is None or dsink.dtype != torch.float32 or dsink.shape != sink.shape or not dsink.is_contiguous() \
+                or dsink.device != q.device:
+            raise RuntimeError("dsink must be a contiguous fp32 tensor shaped like sink")
+        p.dsink = dsink.data_ptr()
     nbytes = l.b200_ffa_bwd_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, q.device)
     p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()

@@ -96,11 +96,18 @@ int check_common(int dtype, int hq, int hk, int d, float softcap) {
   return 0;
 }
 
+int check_sink(const float* sink, int s_sink, int layout) {
+  if (!sink) return 0;
+  if (s_sink < 0 || s_sink > 8) return fail(B200_ERR_INVALID, "seqlen_sink %d must be in [0, 8]", s_sink);
+  if (layout != 0 && layout != 1) return fail(B200_ERR_UNSUPPORTED, "sink_layout %d unsupported (0 = sh, 1 = ssh)", layout);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
 
-const char* b200_ffa_version(void) { return "b200_ffa 0.1.0 sm_100a"; }
+const char* b200_ffa_version(void) { return "b200_ffa 0.2.0 sm_100a"; }
 const char* b200_ffa_last_error(void) { return g_err; }
 int b200_ffa_last_launch_count(void) { return g_launches; }
 
@@ -120,6 +127,8 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   if (p->total_q < 0 || p->total_k < 0 || p->num_slices < 0) return fail(B200_ERR_INVALID, "negative size");
   if (p->total_q == 0) return 0;
   if (!p->q || !p->out || !p->lse) return fail(B200_ERR_INVALID, "null q/out/lse");
+  if (!(p->softmax_scale > 0.f)) return fail(B200_ERR_INVALID, "softmax_scale must be positive");
+  if (int rc = check_sink(p->sink, p->seqlen_sink, p->sink_layout)) return rc;
   if (p->num_slices > 0 && (!p->q_ranges || !p->k_ranges)) return fail(B200_ERR_INVALID, "null ranges");
   if (p->total_k > 0 && (!p->k || !p->v)) return fail(B200_ERR_INVALID, "null k/v");
   const size_t o_align = p->out_dtype == B200_F32 ? 16 : 16;
@@ -145,7 +154,7 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   if (int rc = make_map_thd(&tmQ, p->q, p->dtype, p->head_dim, p->total_q, p->num_heads_q, p->q_stride_t, p->q_stride_h, 128, "q")) return rc;
   // k/v may legally be empty (total_k == 0): point the maps at q so encoding succeeds; no block is ever loaded.
   const bool kv_empty = p->total_k == 0;
-  const int kv_box_rows = (fwd_variant() == 64 && p->head_dim == 128) ? 64 : 128;
+  const int kv_box_rows = (fwd_variant() == 64 && p->head_dim == 128 && !p->max_logits) ? 64 : 128;
   if (int rc = make_map_thd(&tmK, kv_empty ? p->q : p->k, p->dtype, p->head_dim, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
                             kv_empty ? p->q_stride_t : p->k_stride_t, kv_empty ? p->q_stride_h : p->k_stride_h, kv_box_rows, "k")) return rc;
   if (int rc = make_map_thd(&tmV, kv_empty ? p->q : p->v, p->dtype, p->head_dim, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
@@ -167,12 +176,19 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   a.lse_stride_h = p->lse_stride_h;
   a.scale = p->softmax_scale;
   a.accumulate = p->accumulate;
-  // the 64-column experimental variant exists for head_dim 128 only
-  e = (fwd_variant() == 64 && p->head_dim == 128)
+  a.max_logits = p->max_logits;
+  // the 64-column experimental variant exists for head_dim 128 only and does not track max_logits
+  e = (fwd_variant() == 64 && p->head_dim == 128 && !p->max_logits)
           ? ffa::launch_fwd64(p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream)
           : ffa::launch_fwd(p->head_dim, p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream);
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "fwd launch: %s", cudaGetErrorString(e));
   ++g_launches;
+  if (p->sink && p->seqlen_sink > 0) {
+    e = ffa::launch_sink_fwd(p->out_dtype, p->out, p->lse, p->sink, p->total_q, p->num_heads_q, p->head_dim, p->seqlen_sink,
+                             p->sink_layout, p->o_stride_t, p->o_stride_h, p->lse_stride_t, p->lse_stride_h, stream);
+    if (e != cudaSuccess) return fail(B200_ERR_CUDA, "sink fwd launch: %s", cudaGetErrorString(e));
+    ++g_launches;
+  }
   return 0;
 }
 
@@ -200,7 +216,11 @@ int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream_) {
   if (p->total_q > 0 && (!p->q || !p->dout || !p->out || !p->lse || !p->dq)) return fail(B200_ERR_INVALID, "null q/dout/out/lse/dq");
   if (p->total_k > 0 && (!p->k || !p->v || !p->dk || !p->dv)) return fail(B200_ERR_INVALID, "null k/v/dk/dv");
   if (p->num_slices > 0 && (!p->q_ranges || !p->k_ranges)) return fail(B200_ERR_INVALID, "null ranges");
-  if (p->total_k == 0) return 0;  // no keys: dq gets no contribution, nothing to write
+  if (int rc = check_sink(p->sink, p->seqlen_sink, p->sink_layout)) return rc;
+  if (p->sink && p->seqlen_sink > 0 && !p->dsink) return fail(B200_ERR_INVALID, "sink given without dsink");
+  if (!(p->softmax_scale > 0.f)) return fail(B200_ERR_INVALID, "softmax_scale must be positive");
+  // no keys: dq gets no contribution, nothing to write (rows that only see the sink have out = 0 => dsink += 0)
+  if (p->total_k == 0) return 0;
   const int esz = p->dkv_dtype == B200_F32 ? 4 : 2;
   if ((reinterpret_cast<uintptr_t>(p->dk) & 15) || (reinterpret_cast<uintptr_t>(p->dv) & 15) || (p->dk_stride_t * esz) % 16 ||
       (p->dk_stride_h * esz) % 16 || (p->dv_stride_t * esz) % 16 || (p->dv_stride_h * esz) % 16)
@@ -236,6 +256,12 @@ int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream_) {
                                  stream);
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "bwd preprocess launch: %s", cudaGetErrorString(e));
   ++g_launches;
+  if (p->sink && p->seqlen_sink > 0 && p->total_q > 0) {
+    e = ffa::launch_sink_bwd(p->dsink, p->sink, p->lse, delta, p->total_q, p->num_heads_q, tq_ld, p->seqlen_sink, p->sink_layout,
+                             p->lse_stride_t, p->lse_stride_h, stream);
+    if (e != cudaSuccess) return fail(B200_ERR_CUDA, "sink bwd launch: %s", cudaGetErrorString(e));
+    ++g_launches;
+  }
 
   CUtensorMap tmQ, tmDO, tmK, tmV, tmDQ;
   const bool q_empty = p->total_q == 0;

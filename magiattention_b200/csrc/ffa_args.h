@@ -16,6 +16,7 @@ struct FwdArgs {
   int64_t o_stride_t, o_stride_h, lse_stride_t, lse_stride_h;
   float scale;       // softmax scale
   int accumulate;
+  float* max_logits; // [num_heads_q] running per-head max of the scaled logits, or nullptr
 };
 
 struct BwdArgs {

@@ -3,11 +3,15 @@
 //    (reference: correct_attn_out_lse Triton kernel, magi_attention/functional/utils.py:364-558);
 //  * b200_range_reduce_sum: row-span scatter-add used by group_reduce's receive side
 //    (reference: range_reduce Triton kernel, magi_attention/common/range_op/_range_reduce.py:360).
+//  * attention-sink post-passes of b200_ffa_fwd / b200_ffa_bwd (launch_sink_fwd / launch_sink_bwd):
+//    reference: sink columns of the fwd postprocess kernel (flash_fwd_postprocess_kernel.h:187-275),
+//    calc_lse_sink / sink_bwd (magi_attention/functional/utils.py:117-206,234-280).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "../../include/b200_ffa.h"
+#include "ffa_kernels.h"
 
 namespace {
 
@@ -33,9 +37,9 @@ __global__ void lse_merge_kernel(TO* __restrict__ out, float* __restrict__ lse, 
   if (mx == -INFINITY) {
     w1 = 0.f; w2 = 0.f; l = -INFINITY;
   } else {
-    l = mx + log1pf(__expf(mn - mx));
-    w1 = l1 == -INFINITY ? 0.f : __expf(l1 - l);
-    w2 = l2 == -INFINITY ? 0.f : __expf(l2 - l);
+    l = mx + log1pf(expf(mn - mx));
+    w1 = l1 == -INFINITY ? 0.f : expf(l1 - l);
+    w2 = l2 == -INFINITY ? 0.f : expf(l2 - l);
   }
   TO* o = out + rh * dim;
   const T2* o2 = out2 + rh * dim;
@@ -71,6 +75,88 @@ __global__ void range_reduce_kernel(TD* __restrict__ dst, const TS* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Attention sink.  The sink is `s_sink` extra logit columns per (row, head) whose value vectors are zero:
+//   lse' = logaddexp(lse, logsumexp_j sink_j),  out' = out * exp(lse - lse').
+// One warp per (row, head) pair; lanes < s_sink hold the sink logits, every lane rescales dim/32 output
+// elements.  layout 0 ("sh"): sink [s_sink, heads]; 1 ("ssh"): sink [rows, s_sink, heads].  HBM-bound.
+// ---------------------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void sink_fwd_kernel(TO* __restrict__ out, float* __restrict__ lse, const float* __restrict__ sink, int64_t rows,
+                                int heads, int dim, int s_sink, int layout, int64_t o_stride_t, int64_t o_stride_h,
+                                int64_t lse_stride_t, int64_t lse_stride_h) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t rh = warp; rh < rows * heads; rh += n_warps) {
+    const int64_t row = rh / heads;
+    const int h = int(rh - row * heads);
+    float sv = -INFINITY;
+    if (lane < s_sink) sv = sink[layout == 0 ? int64_t(lane) * heads + h : (row * s_sink + lane) * heads + h];
+    float mx = sv;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = (lane < s_sink && mx != -INFINITY) ? expf(sv - mx) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    const float lse_sink = mx == -INFINITY ? -INFINITY : mx + logf(se);
+    float* lp = lse + row * lse_stride_t + h * lse_stride_h;
+    const float l = *lp;
+    const float hi = fmaxf(l, lse_sink), lo = fminf(l, lse_sink);
+    const float ln = hi == -INFINITY ? -INFINITY : hi + log1pf(expf(lo - hi));
+    const float w = (l == -INFINITY) ? 0.f : expf(l - ln);
+    TO* op = out + row * o_stride_t + h * o_stride_h;
+    for (int i = lane; i < dim; i += 32) op[i] = from_f<TO>(to_f<TO>(op[i]) * w);
+    if (lane == 0) *lp = ln;
+  }
+}
+
+// dsink = -sum_rows exp(sink - lse) * delta  ("sh": reduced over the rows, fp32 atomicAdd into dsink [s_sink, heads];
+// "ssh": written per row into dsink [rows, s_sink, heads]).  delta [heads, tq_ld] is the backward preprocess
+// output (rowsum(O o dO)); lse is the global lse INCLUDING the sink.  grid (row blocks, heads).
+constexpr int kMaxSink = 8;
+__global__ void sink_bwd_kernel(float* __restrict__ dsink, const float* __restrict__ sink, const float* __restrict__ lse,
+                                const float* __restrict__ delta, int rows, int heads, int tq_ld, int s_sink, int layout,
+                                int64_t lse_stride_t, int64_t lse_stride_h) {
+  const int h = blockIdx.y;
+  float acc[kMaxSink];
+  float sv[kMaxSink];
+#pragma unroll
+  for (int j = 0; j < kMaxSink; ++j) {
+    acc[j] = 0.f;
+    sv[j] = (layout == 0 && j < s_sink) ? sink[int64_t(j) * heads + h] : -INFINITY;
+  }
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += gridDim.x * blockDim.x) {
+    const float l = lse[row * lse_stride_t + h * lse_stride_h];
+    const float nd = -delta[int64_t(h) * tq_ld + row];
+#pragma unroll
+    for (int j = 0; j < kMaxSink; ++j) {
+      if (j < s_sink) {
+        const float s = layout == 0 ? sv[j] : sink[(int64_t(row) * s_sink + j) * heads + h];
+        const float pj = (l == -INFINITY || s == -INFINITY) ? 0.f : expf(s - l);
+        if (layout == 0) acc[j] = fmaf(pj, nd, acc[j]);
+        else dsink[(int64_t(row) * s_sink + j) * heads + h] += pj * nd;
+      }
+    }
+  }
+  if (layout != 0) return;
+  __shared__ float red[kMaxSink][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < kMaxSink; ++j) {
+    float x = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) red[j][wid] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < s_sink) {
+    float x = 0.f;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) x += red[threadIdx.x][w];
+    atomicAdd(&dsink[int64_t(threadIdx.x) * heads + h], x);
+  }
+}
+
 template <typename F>
 int dispatch2(int a, int b, F&& f) {
   auto inner = [&](auto ta) {
@@ -90,6 +176,38 @@ int dispatch2(int a, int b, F&& f) {
 }
 
 }  // namespace
+
+namespace ffa {
+
+cudaError_t launch_sink_fwd(int out_dtype, void* out, float* lse, const float* sink, int64_t rows, int heads, int dim, int s_sink,
+                            int layout, int64_t o_stride_t, int64_t o_stride_h, int64_t lse_stride_t, int64_t lse_stride_h,
+                            cudaStream_t stream) {
+  if (rows * heads == 0 || s_sink == 0) return cudaSuccess;
+  const int threads = 256;
+  const int64_t want = (rows * heads * 32 + threads - 1) / threads;
+  const unsigned blocks = unsigned(want < 148 * 32 ? want : 148 * 32);  // grid-stride beyond 32 CTAs per SM
+#define FFA_SINK_FWD(T_)                                                                                                  \
+  sink_fwd_kernel<T_><<<blocks, threads, 0, stream>>>(static_cast<T_*>(out), lse, sink, rows, heads, dim, s_sink, layout, \
+                                                      o_stride_t, o_stride_h, lse_stride_t, lse_stride_h)
+  if (out_dtype == B200_F32) FFA_SINK_FWD(float);
+  else if (out_dtype == B200_BF16) FFA_SINK_FWD(__nv_bfloat16);
+  else FFA_SINK_FWD(__half);
+#undef FFA_SINK_FWD
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sink_bwd(float* dsink, const float* sink, const float* lse, const float* delta, int rows, int heads, int tq_ld,
+                            int s_sink, int layout, int64_t lse_stride_t, int64_t lse_stride_h, cudaStream_t stream) {
+  if (rows == 0 || heads == 0 || s_sink == 0) return cudaSuccess;
+  const int threads = 256;
+  int bx = (rows + threads * 8 - 1) / (threads * 8);  // ~8 rows per thread before the block reduction
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, heads);
+  sink_bwd_kernel<<<grid, threads, 0, stream>>>(dsink, sink, lse, delta, rows, heads, tq_ld, s_sink, layout, lse_stride_t, lse_stride_h);
+  return cudaGetLastError();
+}
+
+}  // namespace ffa
 
 extern "C" {
 

@@ -122,7 +122,7 @@ __device__ __forceinline__ float2 softmax_half(const uint32_t* sr, float sl2, fl
   return __fadd2_rn(a01, a23);
 }
 
-template <int kD, bool kBF16, bool kOutF32>
+template <int kD, bool kBF16, bool kOutF32, bool kMaxLogits>
 __global__ void __launch_bounds__(fwd::kThreads, 1)
 ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const FwdArgs args) {
@@ -192,6 +192,7 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const float sl2 = args.scale * 1.4426950408889634f;
 
     float m_ref = -INFINITY, l_sum = 0.f;
+    float m_true = -INFINITY;  // exact running max of the raw logits (only consumed by max_logits)
     uint32_t n_act = 0;
     SliceCursor cur;
     cur.init(args.meta, args.plan, tile);
@@ -240,6 +241,7 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           mb = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         }
+        if constexpr (kMaxLogits) m_true = fmaxf(m_true, mb);
         float mneg = (m_ref == -INFINITY) ? 0.f : -m_ref * sl2;
         float2 acc_lo = softmax_half<kBF16>(&sr[0], sl2, mneg, tS);
         const float m_new = fmaxf(m_ref, mb);
@@ -280,6 +282,18 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
 
     // ------------------------------- epilogue -------------------------------
+    if constexpr (kMaxLogits) {
+      // per-head max of the scaled logits over every unmasked (q, k) pair (reference: max_logits of
+      // _flex_flash_attn_forward, flex_flash_attn.py:397-403): warp max, then an ordered-int atomic max
+      float mt = m_true;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+      if (lane == 0 && mt != -INFINITY) {
+        const float val = mt * args.scale;
+        if (val >= 0.f) atomicMax(reinterpret_cast<int*>(args.max_logits + hq), __float_as_int(val));
+        else atomicMin(reinterpret_cast<unsigned int*>(args.max_logits + hq), __float_as_uint(val));
+      }
+    }
     const bool row_ok = row < args.total_q;
     const bool dead = (n_act == 0) || (m_ref == -INFINITY) || !(l_sum > 0.f);
     float lse_new = dead ? -INFINITY : fmaf(m_ref, args.scale, __logf(l_sum));
@@ -523,10 +537,10 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------
-template <int kD, bool kBF16, bool kOutF32>
+template <int kD, bool kBF16, bool kOutF32, bool kMaxLogits>
 static cudaError_t launch_one(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                               const FwdArgs& a, int grid, cudaStream_t stream) {
-  auto kern = ffa_fwd_kernel<kD, kBF16, kOutF32>;
+  auto kern = ffa_fwd_kernel<kD, kBF16, kOutF32, kMaxLogits>;
   constexpr uint32_t smem_bytes = fwd::Cfg<kD>::kSmemBytes;
   static bool attr_set = false;
   if (!attr_set) {
@@ -538,13 +552,21 @@ static cudaError_t launch_one(const CUtensorMap& tmQ, const CUtensorMap& tmK, co
   return cudaGetLastError();
 }
 
+template <int kD, bool kMaxLogits>
+static cudaError_t launch_dm(bool bf16, bool out_f32, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                             const FwdArgs& a, int grid, cudaStream_t stream) {
+  if (bf16) return out_f32 ? launch_one<kD, true, true, kMaxLogits>(tmQ, tmK, tmV, a, grid, stream)
+                           : launch_one<kD, true, false, kMaxLogits>(tmQ, tmK, tmV, a, grid, stream);
+  return out_f32 ? launch_one<kD, false, true, kMaxLogits>(tmQ, tmK, tmV, a, grid, stream)
+                 : launch_one<kD, false, false, kMaxLogits>(tmQ, tmK, tmV, a, grid, stream);
+}
+
+// the max_logits bookkeeping is a separate instantiation so that the common path keeps its register budget
 template <int kD>
 static cudaError_t launch_d(bool bf16, bool out_f32, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                             const FwdArgs& a, int grid, cudaStream_t stream) {
-  if (bf16) return out_f32 ? launch_one<kD, true, true>(tmQ, tmK, tmV, a, grid, stream)
-                           : launch_one<kD, true, false>(tmQ, tmK, tmV, a, grid, stream);
-  return out_f32 ? launch_one<kD, false, true>(tmQ, tmK, tmV, a, grid, stream)
-                 : launch_one<kD, false, false>(tmQ, tmK, tmV, a, grid, stream);
+  return a.max_logits ? launch_dm<kD, true>(bf16, out_f32, tmQ, tmK, tmV, a, grid, stream)
+                      : launch_dm<kD, false>(bf16, out_f32, tmQ, tmK, tmV, a, grid, stream);
 }
 
 cudaError_t launch_fwd(int head_dim, bool bf16, bool out_f32, const CUtensorMap& tmQ, const CUtensorMap& tmK,

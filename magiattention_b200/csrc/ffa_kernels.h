@@ -21,4 +21,10 @@ cudaError_t launch_bwd_preprocess(int head_dim, bool bf16, const void* out, cons
 cudaError_t launch_bwd(int head_dim, bool bf16, bool dkv_f32, const CUtensorMap& tmQ, const CUtensorMap& tmDO,
                        const CUtensorMap& tmK, const CUtensorMap& tmV, const CUtensorMap& tmDQ, const BwdArgs& a,
                        cudaStream_t stream);
+// attention-sink post-passes (ffa_aux.cu); layout 0 = "sh" [s_sink, heads], 1 = "ssh" [rows, s_sink, heads]
+cudaError_t launch_sink_fwd(int out_dtype, void* out, float* lse, const float* sink, int64_t rows, int heads, int dim, int s_sink,
+                            int layout, int64_t o_stride_t, int64_t o_stride_h, int64_t lse_stride_t, int64_t lse_stride_h,
+                            cudaStream_t stream);
+cudaError_t launch_sink_bwd(float* dsink, const float* sink, const float* lse, const float* delta, int rows, int heads, int tq_ld,
+                            int s_sink, int layout, int64_t lse_stride_t, int64_t lse_stride_h, cudaStream_t stream);
 }  // namespace ffa

@@ -20,6 +20,8 @@ docs/source/blog/magi_attn.md:273-275).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -68,17 +70,45 @@ class DistAttnRuntime:
         return group_reduce((dk_part, dv_part), (dk, dv), group=self.cp_group, async_op=True, reduce_op="sum",
                             acc_reduce=True, **arg.to_group_reduce_args())
 
-    # ---- compute -----------------------------------------------------------------------------------
-    def attn_fwd(self, q, k, v, arg: AttnArg, out_acc, lse_acc, softmax_scale, softcap):
-        if arg.can_skip:
-            return
-        a = arg.to_ffa_args(q.device)
-        _flex_flash_attn_forward(q, k, v, None, "sh", out_acc, lse_acc, a["q_ranges"], a["k_ranges"], a["attn_type_map"],
-                                 softmax_scale, softcap, torch.float32, sm_margin=self.sm_margin)
+    def reduce_max_logits(self, max_logits: torch.Tensor | None) -> torch.Tensor | None:
+        """Element-wise MAX over the cp group (reference: reduce_max_logits :532-555)."""
+        if max_logits is not None and self.cp_group is not None and self.cp_size > 1:
+            dist.all_reduce(max_logits, op=dist.ReduceOp.MAX, group=self.cp_group)
+        return max_logits
 
-    def attn_bwd(self, do, q, k, v, out, lse, arg: AttnArg, dq_acc, dk, dv, softmax_scale, softcap):
-        a = arg.to_ffa_args(q.device)
-        _flex_flash_attn_backward(do, q, k, v, None, "sh", out, lse, dq_acc, dk, dv, None, a["q_ranges"], a["k_ranges"],
+    def reduce_partial_dsink(self, dsink: torch.Tensor | None) -> torch.Tensor | None:
+        """The sink is replicated, every rank holds the partial gradient of its own rows.  Like the reference
+        (env/comm.py:137-168, dist_attn.py:882-896) the cross-rank reduction is opt-in through
+        MAGI_ATTENTION_DSINK_ALL_REDUCE_OP in {none (default: the training framework reduces parameters), sum, avg}."""
+        op = os.environ.get("MAGI_ATTENTION_DSINK_ALL_REDUCE_OP", "none")
+        assert op in ("none", "sum", "avg"), f"Invalid value of MAGI_ATTENTION_DSINK_ALL_REDUCE_OP: {op}"
+        if dsink is not None and op != "none" and self.cp_group is not None and self.cp_size > 1:
+            dist.all_reduce(dsink, op=dist.ReduceOp.SUM, group=self.cp_group)
+            if op == "avg":
+                dsink /= self.cp_size
+        return dsink
+
+    # ---- compute -----------------------------------------------------------------------------------
+    @staticmethod
+    def _ffa_args(arg: AttnArg, device) -> dict:
+        if arg.can_skip:  # no slices: the kernels still define uncovered rows (out 0 / lse -inf) and apply the sink
+            e = torch.empty((0, 2), dtype=torch.int32, device=device)
+            return {"q_ranges": e, "k_ranges": e, "attn_type_map": torch.empty((0,), dtype=torch.int32, device=device)}
+        return arg.to_ffa_args(device)
+
+    def attn_fwd(self, q, k, v, arg: AttnArg, out_acc, lse_acc, softmax_scale, softcap, sink=None, max_logits=None):
+        """One stage into the fp32 accumulators.  ``sink`` is passed on the host stage only: it must be applied
+        exactly once (reference :1278-1280), and then also when the host stage has no slices (:2380-2408)."""
+        if arg.can_skip and sink is None:
+            return
+        a = self._ffa_args(arg, q.device)
+        _flex_flash_attn_forward(q, k, v, sink, "sh", out_acc, lse_acc, a["q_ranges"], a["k_ranges"], a["attn_type_map"],
+                                 softmax_scale, softcap, torch.float32, sm_margin=self.sm_margin,
+                                 return_max_logits=max_logits is not None, max_logits=max_logits)
+
+    def attn_bwd(self, do, q, k, v, out, lse, arg: AttnArg, dq_acc, dk, dv, softmax_scale, softcap, sink=None, dsink=None):
+        a = self._ffa_args(arg, q.device)
+        _flex_flash_attn_backward(do, q, k, v, sink, "sh", out, lse, dq_acc, dk, dv, dsink, a["q_ranges"], a["k_ranges"],
                                   a["attn_type_map"], softmax_scale, softcap, sm_margin=self.sm_margin)
 
 
@@ -86,28 +116,34 @@ class DistAttnFunc(torch.autograd.Function):
     """Reference: DistAttnFunc.forward :2997-3194 / backward :3455-3605."""
 
     @staticmethod
-    def forward(ctx, q, k, v, runtime: DistAttnRuntime, softmax_scale, softcap):
+    def forward(ctx, q, k, v, sink, runtime: DistAttnRuntime, softmax_scale, softcap, return_max_logits):
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         cm = runtime.calc_meta
         works = runtime.fetch_remote_kv(k, v)
         out_acc = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
         lse_acc = torch.full((q.shape[0], q.shape[1]), float("-inf"), dtype=torch.float32, device=q.device)
-        runtime.attn_fwd(q, k, v, cm.local_attn_arg, out_acc, lse_acc, softmax_scale, softcap)
+        max_logits = (torch.full((q.shape[1],), float("-inf"), dtype=torch.float32, device=q.device)
+                      if return_max_logits else None)
+        runtime.attn_fwd(q, k, v, cm.local_attn_arg, out_acc, lse_acc, softmax_scale, softcap, sink=sink, max_logits=max_logits)
         for st in range(runtime.overlap_degree):
             w = works[st]
             if w is None:
                 continue
             rk, rv = w.wait_post_process()
-            runtime.attn_fwd(q, rk, rv, cm.remote_attn_args_list[st], out_acc, lse_acc, softmax_scale, softcap)
+            runtime.attn_fwd(q, rk, rv, cm.remote_attn_args_list[st], out_acc, lse_acc, softmax_scale, softcap,
+                             max_logits=max_logits)
+        max_logits = runtime.reduce_max_logits(max_logits)
         out = out_acc.to(q.dtype)
-        ctx.save_for_backward(q, k, v, out, lse_acc)
+        ctx.save_for_backward(q, k, v, sink, out, lse_acc)
         ctx.runtime, ctx.softmax_scale, ctx.softcap = runtime, softmax_scale, softcap
         ctx.mark_non_differentiable(lse_acc)
-        return out, lse_acc
+        if max_logits is not None:
+            ctx.mark_non_differentiable(max_logits)
+        return out, lse_acc, max_logits
 
     @staticmethod
     def backward(ctx, dout, *args):
-        q, k, v, out, lse = ctx.saved_tensors
+        q, k, v, sink, out, lse = ctx.saved_tensors
         runtime: DistAttnRuntime = ctx.runtime
         cm = runtime.calc_meta
         scale, softcap = ctx.softmax_scale, ctx.softcap
@@ -116,8 +152,10 @@ class DistAttnFunc(torch.autograd.Function):
         dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
         dk = torch.zeros(k.shape, dtype=torch.float32, device=k.device)
         dv = torch.zeros(v.shape, dtype=torch.float32, device=v.device)
-        if not cm.local_attn_arg.can_skip:
-            runtime.attn_bwd(dout, q, k, v, out, lse, cm.local_attn_arg, dq, dk, dv, scale, softcap)
+        dsink = torch.zeros_like(sink, dtype=torch.float32) if sink is not None else None
+        if not cm.local_attn_arg.can_skip or sink is not None:
+            # the host stage also produces this rank's partial dsink (rows it owns; reference :663-713)
+            runtime.attn_bwd(dout, q, k, v, out, lse, cm.local_attn_arg, dq, dk, dv, scale, softcap, sink=sink, dsink=dsink)
         reduces: list[WorkWithPostProcessFn] = []
         wire = torch.float32 if runtime.high_precision_reduce else k.dtype
         for st in range(runtime.overlap_degree):
@@ -140,16 +178,21 @@ class DistAttnFunc(torch.autograd.Function):
             reduces.append(runtime.reduce_partial_dkv(st, dk_p, dv_p, dk, dv))
         for rw in reduces:
             rw.wait_post_process()
-        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None, None
+        dsink = runtime.reduce_partial_dsink(dsink)
+        if dsink is not None:
+            dsink = dsink.to(sink.dtype)
+        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), dsink, None, None, None, None
 
 
 def dist_attn_func(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, dist_attn_runtime: DistAttnRuntime,
                    sink: torch.Tensor | None = None, softmax_scale: float | None = None, softcap: float = 0.0,
                    return_max_logits: bool = False) -> tuple[torch.Tensor, AttnForwardMeta]:
     """Local shards in, local attention out (reference signature: dist_attn.py:3608-3680)."""
-    if sink is not None or return_max_logits or softcap != 0.0:
-        raise RuntimeError("B200 backend does not support sink / return_max_logits / softcap")
+    if softcap != 0.0:
+        raise RuntimeError("B200 backend does not support softcap")
+    if sink is not None and sink.dim() != 2:
+        raise RuntimeError('dist_attn_func takes a replicated sink with layout "sh": [num_tokens_sink, num_heads_q]')
     if softmax_scale is None:
         softmax_scale = q.shape[-1] ** (-0.5)
-    out, lse = DistAttnFunc.apply(q, k, v, dist_attn_runtime, softmax_scale, softcap)
-    return out, AttnForwardMeta(lse=lse, max_logits=None)
+    out, lse, max_logits = DistAttnFunc.apply(q, k, v, sink, dist_attn_runtime, softmax_scale, softcap, return_max_logits)
+    return out, AttnForwardMeta(lse=lse, max_logits=max_logits)

@@ -12,8 +12,10 @@ Differences that are deliberate:
     ``disable_bwd_dkv_atomic_reduction``, ``deterministic`` (always deterministic except the fp32 dQ
     reduction order), ``ref_block_size``, ``max_seqlen_q``, ``swap_ab``, ``pack_gqa``, ``cat_gqa``,
     ``swap_bwd_qk_loop``, ``auto_range_merge`` are accepted and have no effect on results;
-  * unsupported knobs raise like the reference's FA4 guard does (:1399-1421): ``sink``, ``softcap``,
-    ``sparse_load``, ``index_attn`` / ``index_attn_indices``, ``return_max_logits``.
+  * unsupported knobs raise like the reference's FA4 guard does (:1399-1421): ``softcap``,
+    ``sparse_load``, ``index_attn`` / ``index_attn_indices``, sink layout ``"shd"``.
+Attention ``sink`` (fp32, layouts ``"sh"`` / ``"ssh"``, at most 8 sink tokens like the reference kernel) and
+``return_max_logits`` are supported.
 """
 from __future__ import annotations
 
@@ -61,11 +63,14 @@ def _flex_flash_attn_forward(
     previous partial result (over a disjoint key set) and are LSE-merged in place with this call's
     result inside the kernel epilogue (reference: dist_attn.py:1296-1297; pinned by
     tests/test_attn/test_flex_flash_attn.py:362-540)."""
-    if sink is not None:
-        raise RuntimeError("B200 FFA backend does not support attention sink")
-    if unused.get("return_max_logits") or unused.get("sparse_load") or unused.get("index_attn"):
-        raise RuntimeError("B200 FFA backend does not support return_max_logits / sparse_load / index_attn")
-    q, k, v, q_ranges, k_ranges = (_maybe_contiguous(x) for x in (q, k, v, q_ranges, k_ranges))
+    if unused.get("sparse_load") or unused.get("index_attn"):
+        raise RuntimeError("B200 FFA backend does not support sparse_load / index_attn")
+    return_max_logits = bool(unused.get("return_max_logits", False))
+    max_logits = unused.get("max_logits")
+    if return_max_logits and max_logits is None:
+        # reference: flex_flash_attn.py:397-403 — a fresh buffer starts at -inf, a given one is max-reduced into
+        max_logits = torch.full((q.size(1),), float("-inf"), dtype=torch.float32, device=q.device)
+    q, k, v, sink, q_ranges, k_ranges = (_maybe_contiguous(x) for x in (q, k, v, sink, q_ranges, k_ranges))
     _check_ranges(q_ranges, k_ranges, attn_type_map)
     accumulate = out is not None
     if (out is None) != (lse is None):
@@ -74,8 +79,9 @@ def _flex_flash_attn_forward(
         out = torch.empty_like(q, dtype=out_type or q.dtype)
         lse = torch.empty((q.size(0), q.size(1)), dtype=torch.float32, device=q.device)
     _lib.ffa_fwd(q, k, v, out, lse, q_ranges, k_ranges, attn_type_map, softmax_scale, softcap,
-                 accumulate=accumulate, sm_margin=sm_margin)
-    return out, AttnForwardMeta(lse=lse, max_logits=None)
+                 accumulate=accumulate, sm_margin=sm_margin, sink=sink, sink_layout=sink_layout,
+                 max_logits=max_logits if return_max_logits else None)
+    return out, AttnForwardMeta(lse=lse, max_logits=max_logits if return_max_logits else None)
 
 
 def _flex_flash_attn_backward(
@@ -103,13 +109,15 @@ def _flex_flash_attn_backward(
     deterministic: bool = False,
     sm_margin: int = 0,
     **unused,
-) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, None]:
+) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor | None]:
     """Raw backward launcher.  ``out``/``lse`` are the GLOBAL forward results, so partial gradients over
     disjoint key sets add exactly.  A given fp32 ``dq`` is accumulated into; given fp32 ``dk``/``dv`` are
-    accumulated into as well (reference: flex_flash_attn.py:637-647, dist_attn.py:1432)."""
-    if sink is not None:
-        raise RuntimeError("B200 FFA backend does not support attention sink")
-    dout, q, k, v, out, q_ranges, k_ranges = (_maybe_contiguous(x) for x in (dout, q, k, v, out, q_ranges, k_ranges))
+    accumulated into as well (reference: flex_flash_attn.py:637-647, dist_attn.py:1432).  With a ``sink`` the
+    fp32 ``dsink`` (zero-initialised when not given, :652-657) is accumulated into and returned."""
+    dout, q, k, v, sink, out, q_ranges, k_ranges = (
+        _maybe_contiguous(x) for x in (dout, q, k, v, sink, out, q_ranges, k_ranges))
+    if sink is not None and dsink is None:
+        dsink = torch.zeros_like(sink, dtype=torch.float32)
     _check_ranges(q_ranges, k_ranges, attn_type_map)
     if out.dtype != q.dtype:
         out = out.to(q.dtype)
@@ -124,32 +132,38 @@ def _flex_flash_attn_backward(
         dk = torch.empty_like(k, dtype=dk_type or torch.float32)
         dv = torch.empty_like(v, dtype=dv_type or torch.float32)
     _lib.ffa_bwd(dout, q, k, v, out, lse, dq, dk, dv, q_ranges, k_ranges, attn_type_map, softmax_scale, softcap,
-                 accumulate_dkv=accumulate_dkv, sm_margin=sm_margin)
-    return dq, dk, dv, None
+                 accumulate_dkv=accumulate_dkv, sm_margin=sm_margin, sink=sink, sink_layout=sink_layout,
+                 dsink=dsink if sink is not None else None)
+    return dq, dk, dv, (dsink if sink is not None else None)
 
 
 class FlexFlashAttnFunc(torch.autograd.Function):
     """Autograd glue (reference: FlexFlashAttnFunc, flex_flash_attn.py:699-1060)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, q_ranges, k_ranges, attn_type_map, softmax_scale, softcap, sm_margin):
+    def forward(ctx, q, k, v, sink, sink_layout, q_ranges, k_ranges, attn_type_map, softmax_scale, softcap, sm_margin,
+                return_max_logits):
         out, meta = _flex_flash_attn_forward(
-            q, k, v, None, "sh", None, None, q_ranges, k_ranges, attn_type_map, softmax_scale, softcap,
-            out_type=q.dtype, sm_margin=sm_margin,
+            q, k, v, sink, sink_layout, None, None, q_ranges, k_ranges, attn_type_map, softmax_scale, softcap,
+            out_type=q.dtype, sm_margin=sm_margin, return_max_logits=return_max_logits,
         )
-        ctx.save_for_backward(q, k, v, out, meta.lse, q_ranges, k_ranges, attn_type_map)
-        ctx.softmax_scale, ctx.softcap, ctx.sm_margin = softmax_scale, softcap, sm_margin
+        ctx.save_for_backward(q, k, v, sink, out, meta.lse, q_ranges, k_ranges, attn_type_map)
+        ctx.softmax_scale, ctx.softcap, ctx.sm_margin, ctx.sink_layout = softmax_scale, softcap, sm_margin, sink_layout
         ctx.mark_non_differentiable(meta.lse)
-        return out, meta.lse
+        if meta.max_logits is not None:
+            ctx.mark_non_differentiable(meta.max_logits)
+        return out, meta.lse, meta.max_logits
 
     @staticmethod
     def backward(ctx, dout, *args):
-        q, k, v, out, lse, q_ranges, k_ranges, attn_type_map = ctx.saved_tensors
-        dq, dk, dv, _ = _flex_flash_attn_backward(
-            dout, q, k, v, None, "sh", out, lse, None, None, None, None, q_ranges, k_ranges, attn_type_map,
+        q, k, v, sink, out, lse, q_ranges, k_ranges, attn_type_map = ctx.saved_tensors
+        dq, dk, dv, dsink = _flex_flash_attn_backward(
+            dout, q, k, v, sink, ctx.sink_layout, out, lse, None, None, None, None, q_ranges, k_ranges, attn_type_map,
             ctx.softmax_scale, ctx.softcap, dk_type=k.dtype, dv_type=v.dtype, sm_margin=ctx.sm_margin,
         )
-        return dq.to(q.dtype), dk, dv, None, None, None, None, None, None
+        if dsink is not None:
+            dsink = dsink.to(sink.dtype)
+        return dq.to(q.dtype), dk, dv, dsink, None, None, None, None, None, None, None, None
 
 
 def flex_flash_attn_func(
@@ -191,8 +205,8 @@ def flex_flash_attn_func(
         "Exactly one of (q_ranges + k_ranges) or index_attn_indices must be provided."
     )
     bad = [name for name, on in {
-        "index_attn_indices": index_attn_indices is not None, "sink": sink is not None, "softcap": softcap != 0.0,
-        "sparse_load": sparse_load, "index_attn": index_attn, "return_max_logits": return_max_logits,
+        "index_attn_indices": index_attn_indices is not None, "softcap": softcap != 0.0,
+        "sparse_load": sparse_load, "index_attn": index_attn,
     }.items() if on]
     assert not bad, f"B200 FFA backend does not support the following features: {bad}."
     assert k_ranges is not None, "k_ranges must be provided together with q_ranges"
@@ -200,5 +214,8 @@ def flex_flash_attn_func(
     assert q.dim() == 3 and k.dim() == 3 and v.dim() == 3, "q/k/v must be [tokens, heads, head_dim]"
     if softmax_scale is None:
         softmax_scale = q.shape[-1] ** (-0.5)
-    out, lse = FlexFlashAttnFunc.apply(q, k, v, q_ranges, k_ranges, attn_type_map, softmax_scale, softcap, sm_margin)
-    return out, AttnForwardMeta(lse=lse, max_logits=None)
+    if return_max_logits:
+        assert q.size(1) <= 128, f"num_qheads ({q.size(1)}) must be <= 128 when return_max_logits is set"  # reference :404-409
+    out, lse, max_logits = FlexFlashAttnFunc.apply(
+        q, k, v, sink, sink_layout, q_ranges, k_ranges, attn_type_map, softmax_scale, softcap, sm_margin, return_max_logits)
+    return out, AttnForwardMeta(lse=lse, max_logits=max_logits)

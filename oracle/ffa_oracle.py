@@ -99,6 +99,18 @@ def _expand_kv(x: torch.Tensor, rep: int) -> torch.Tensor:
     return x.repeat_interleave(rep, dim=1) if rep > 1 else x
 
 
+def _sink_hqs(sink: torch.Tensor, tq: int, sink_layout: str) -> torch.Tensor:
+    """sink -> [hq, tq, s_sink] (testing/ref_attn.py:466-477): "sh" [s_sink, hq] is broadcast over the rows,
+    "ssh" [tq, s_sink, hq] is per row."""
+    if sink_layout == "sh":
+        assert sink.dim() == 2
+        return sink.t().unsqueeze(1).expand(-1, tq, -1)
+    if sink_layout == "ssh":
+        assert sink.dim() == 3 and sink.shape[0] == tq
+        return sink.permute(2, 0, 1)
+    raise NotImplementedError(f"sink_layout {sink_layout} is not supported yet")
+
+
 def attn_fwd(
     q: torch.Tensor,
     k: torch.Tensor,
@@ -106,6 +118,8 @@ def attn_fwd(
     mask: torch.Tensor,
     softmax_scale: float | None = None,
     high_precision: bool = True,
+    sink: torch.Tensor | None = None,
+    sink_layout: str = "sh",
 ) -> tuple[torch.Tensor, torch.Tensor]:
     """O [tq,hq,d] (q dtype) and LSE [tq,hq] fp32 (natural log).
 
@@ -114,6 +128,8 @@ def attn_fwd(
     S = Q K^T * scale + bias; LSE = logsumexp(S); P = exp(S - LSE) cast to q dtype; O = P V;
     rows with no unmasked key give O = 0, LSE = -inf.  ``high_precision`` computes in fp64
     (ref_attn.py:715-719), else in the input dtype (the "low-precision reference").
+    ``sink`` (ref_attn.py:546-563): S is widened by the sink logit columns before the softmax and the sink
+    columns of P are dropped before P V — sink tokens take probability mass but carry no value.
     """
     org = q.dtype
     mask = mask.to(q.device)
@@ -130,10 +146,17 @@ def attn_fwd(
     s = qh @ kt * scale
     s = s.to(torch.float64 if high_precision else torch.float32)
     s = s.masked_fill(~mask.unsqueeze(0), NEG_INF)
+    n_sink = 0
+    if sink is not None:
+        sk = _sink_hqs(sink.to(s.device), tq, sink_layout).to(s.dtype)
+        n_sink = sk.shape[-1]
+        s = torch.cat([s, sk], dim=-1)
     dead = (s == NEG_INF).all(dim=-1, keepdim=True)
     lse = torch.logsumexp(s, dim=-1, keepdim=True).masked_fill(dead, NEG_INF)
     p = torch.exp(torch.where(s == NEG_INF, s, s - torch.where(dead, torch.zeros_like(lse), lse)))
     p = p.masked_fill(dead, 0.0).to(qh.dtype)
+    if n_sink:
+        p = p[..., :-n_sink]
     out = p @ vh
     out = out.permute(1, 0, 2).contiguous().to(org)
     lse = lse.squeeze(-1).t().contiguous()
@@ -190,6 +213,31 @@ def attn_bwd(
         dv = dv.reshape(hk, rep, *dv.shape[1:]).sum(1)
     perm = lambda x: x.permute(1, 0, 2).contiguous().to(org)
     return perm(dq), perm(dk), perm(dv)
+
+
+def sink_bwd(sink: torch.Tensor, lse: torch.Tensor, out: torch.Tensor, do: torch.Tensor, sink_layout: str = "sh") -> torch.Tensor:
+    """dsink in the layout of ``sink`` (fp64).  Restates functional/utils.py:117-206:
+    p_sink = exp(sink - lse) (0 where lse = -inf), delta = rowsum(O o dO), dsink = -p_sink * delta, summed over
+    the rows for "sh".  ``lse`` is the global lse that already includes the sink."""
+    tq = lse.shape[0]
+    sk = _sink_hqs(sink.double().to(lse.device), tq, sink_layout)  # [hq, tq, s]
+    l = lse.double().t().unsqueeze(-1)  # [hq, tq, 1]
+    delta = (out.double() * do.double()).sum(-1).t().unsqueeze(-1)  # [hq, tq, 1]
+    dead = l == NEG_INF
+    p = torch.exp(sk - torch.where(dead, torch.zeros_like(l), l)).masked_fill(dead, 0.0)
+    d = p * -delta
+    return d.sum(dim=1).t().contiguous() if sink_layout == "sh" else d.permute(1, 2, 0).contiguous()
+
+
+def max_logits(q: torch.Tensor, k: torch.Tensor, mask: torch.Tensor, softmax_scale: float | None = None) -> torch.Tensor:
+    """Per-head max of the scaled logits over the unmasked pairs, [hq] (-inf for an empty mask).
+    Restates testing/ref_attn.py:368-391 (_calc_attn_max_logits)."""
+    tq, hq, d = q.shape
+    scale = d ** -0.5 if softmax_scale is None else softmax_scale
+    ke = _expand_kv(k, hq // k.shape[1])
+    s = (q.permute(1, 0, 2) @ ke.permute(1, 2, 0) * scale).to(torch.float64 if q.dtype == torch.float64 else torch.float32)
+    s = s.masked_fill(~mask.to(q.device).unsqueeze(0), NEG_INF)
+    return s.reshape(hq, -1).max(dim=-1).values if s.numel() else torch.full((hq,), NEG_INF, dtype=s.dtype, device=q.device)
 
 
 def merge_out_lse(
@@ -304,7 +352,7 @@ def group_reduce_ref(
 NORM_RTOL_RATIO = 2.0  # testing/precision.py:36
 MISMATCH_THRES_RATIO = 2.0
 MAX_MISMATCH_THRES = 0.75
-RTOL = {"out": 0.05, "lse": 1e-3, "dq": 0.3, "dk": 0.15, "dv": 0.05}
+RTOL = {"out": 0.05, "lse": 1e-3, "dq": 0.3, "dk": 0.15, "dv": 0.05, "dsink": 0.1}  # dsink: test_flex_flash_attn.py:1768
 ATOL = 1e-8
 
 
@@ -320,6 +368,13 @@ def grad_atol(ref: torch.Tensor) -> float:
     return ATOL + 2e-5 * float(ref.abs().max())
 
 
+def dsink_atol(ref: torch.Tensor) -> float:
+    """Absolute epsilon for dsink: the reference's 2e-4 (tests/test_attn/test_flex_flash_attn.py:1767) or 2^-8 of the
+    largest element, whichever is larger — dsink (layout "sh") is a signed sum over every row, so an element that
+    cancels to ~0 still carries the 16-bit rounding error of its summands (rowsum(O o dO) uses the rounded O)."""
+    return max(2e-4, 2.0 ** -8 * float(ref.detach().abs().max())) if ref.numel() else 2e-4
+
+
 def _mismatch_ratio(a: torch.Tensor, ref: torch.Tensor, atol: float, rtol: float) -> float:
     a, ref = a.double(), ref.double()
     both_inf = torch.isinf(a) & torch.isinf(ref) & (a == ref)
@@ -332,11 +387,11 @@ def _mismatch_ratio(a: torch.Tensor, ref: torch.Tensor, atol: float, rtol: float
 def _inf_norm(x: torch.Tensor) -> float:
     x = x.double()
     x = torch.where(torch.isinf(x), torch.zeros_like(x), x)
-    return float(x.abs().max()) if x.numel() else 0.0
+    return float(x.detach().abs().max()) if x.numel() else 0.0
 
 
 def check_close(name: str, test: torch.Tensor, ref_hp: torch.Tensor, ref_lp: torch.Tensor, kind: str,
-                atol: float = ATOL) -> dict:
+                atol: float = ATOL, min_mismatch: float = 1e-4, norm_floor: float | None = None) -> dict:
     """The reference's two-sided rule: ||test-ref64||inf <= 2*||ref_lp-ref64||inf AND
     mismatch(test) <= max(2*mismatch(ref_lp), small floor) capped at 0.75.
     Returns a report dict; raises AssertionError on violation.
@@ -354,9 +409,10 @@ def check_close(name: str, test: torch.Tensor, ref_hp: torch.Tensor, ref_lp: tor
     rtol = RTOL[kind]
     mm_t = _mismatch_ratio(t, hp, atol, rtol)
     mm_lp = _mismatch_ratio(lp, hp, atol, rtol)
-    thres = min(max(MISMATCH_THRES_RATIO * mm_lp, 1e-4), MAX_MISMATCH_THRES)
+    thres = min(max(MISMATCH_THRES_RATIO * mm_lp, min_mismatch), MAX_MISMATCH_THRES)
     rep = dict(name=name, norm=norm_t, norm_ref=norm_lp, mismatch=mm_t, mismatch_ref=mm_lp, thres=thres)
-    norm_floor = 1e-6 if kind == "lse" else 0.0
+    if norm_floor is None:
+        norm_floor = 1e-6 if kind == "lse" else 0.0
     assert norm_t <= NORM_RTOL_RATIO * norm_lp + norm_floor, f"{name}: inf-norm {norm_t:.3e} > 2 x {norm_lp:.3e} ({rep})"
     assert mm_t <= thres, f"{name}: mismatch ratio {mm_t:.3e} > {thres:.3e} ({rep})"
     return rep

@@ -76,7 +76,7 @@ def test_ctypes_struct_matches_header(cname, pyname):
 def test_version_and_workspace_sizing(lib):
     from magiattention_b200 import _lib
 
-    assert lib.b200_ffa_version().decode() == "b200_ffa 0.1.0 sm_100a"
+    assert lib.b200_ffa_version().decode() == "b200_ffa 0.2.0 sm_100a"
     p = _lib.FwdParams()
     p.total_q, p.num_slices = 262144, 1
     w1 = lib.b200_ffa_fwd_workspace_bytes(C.byref(p))

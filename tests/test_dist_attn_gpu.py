@@ -111,7 +111,7 @@ def _free_port():
     return p
 
 
-def _cp_worker(rank, world, port, name):
+def _cp_worker(rank, world, port, name, with_sink=False):
     import torch.distributed as dist
     from magiattention_b200.api import calc_attn, compute_pad_size, dispatch, magi_attn_flex_key, undispatch
     from magiattention_b200.common import AttnRanges
@@ -129,17 +129,29 @@ def _cp_worker(rank, world, port, name):
         for x in (q, k, v, do):
             dist.broadcast(x, 0)
         q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
+        sink = None
+        if with_sink:
+            os.environ["MAGI_ATTENTION_DSINK_ALL_REDUCE_OP"] = "sum"
+            sink = torch.randn(4, H, dtype=torch.float32, device=dev)
+            dist.broadcast(sink, 0)
+            sink.requires_grad_(True)
         key = magi_attn_flex_key(AttnRanges.from_ranges(cfg["q_ranges"]), AttnRanges.from_ranges(cfg["k_ranges"]), cfg["types"],
                                  T, T, H, HK, D, pad, dist.group.WORLD, chunk_size=chunk)
         ql, kl, vl = dispatch(q, key), dispatch(k, key), dispatch(v, key)
-        ol, meta = calc_attn(ql, kl, vl, key)
+        ol, meta = calc_attn(ql, kl, vl, key, sink=sink, return_max_logits=with_sink)
         out = undispatch(ol, key)
         out.backward(do)
         mask = orc.mask_from_slices(cfg["q_ranges"], cfg["k_ranges"], cfg["types"], T, T)
         qd, kd, vd = q.detach(), k.detach(), v.detach()
-        ro, rl = orc.attn_fwd(qd, kd, vd, mask, high_precision=True)
-        lo, ll = orc.attn_fwd(qd, kd, vd, mask, high_precision=False)
+        sd = sink.detach() if with_sink else None
+        ro, rl = orc.attn_fwd(qd, kd, vd, mask, high_precision=True, sink=sd)
+        lo, ll = orc.attn_fwd(qd, kd, vd, mask, high_precision=False, sink=sd)
         orc.check_close("out", out.detach(), ro, lo, "out")
+        if with_sink:
+            torch.testing.assert_close(meta.max_logits.double(), orc.max_logits(qd.double(), kd.double(), mask), atol=1e-4, rtol=1e-5)
+            ds_ref, ds_lp = orc.sink_bwd(sd, rl, ro, do, "sh"), orc.sink_bwd(sd, ll, lo, do, "sh")
+            orc.check_close("dsink", sink.grad, ds_ref, ds_lp.float(), "dsink", atol=orc.dsink_atol(ds_ref),
+                            min_mismatch=max(1.0 / ds_ref.numel(), 8e-2), norm_floor=0.015)
         ref = orc.attn_bwd(do, qd, kd, vd, ro.double(), rl.double(), mask, high_precision=True)
         lp = orc.attn_bwd(do, qd, kd, vd, lo, ll, mask, high_precision=False)
         for nm, g, r_, l_ in zip(("dq", "dk", "dv"), (q.grad, k.grad, v.grad), ref, lp):
@@ -156,3 +168,16 @@ def test_real_cp_nccl(name):
 
     world = min(torch.cuda.device_count(), 4)
     mp.spawn(_cp_worker, args=(world, _free_port(), name), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("name", ["uncovered_rows", "all_types_aspects"])
+def test_real_cp_nccl_sink_and_max_logits(name):
+    """calc_attn(sink=..., return_max_logits=True) through the runtime with the real kernels: sink applied once on the host
+    stage, per-rank partial dsink all-reduced (MAGI_ATTENTION_DSINK_ALL_REDUCE_OP=sum), max_logits MAX-reduced.  Runs at
+    cp = 1 on a single GPU (stage loop degenerate, same code path) and at cp = min(#GPUs, 4) otherwise."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 4)
+    mp.spawn(_cp_worker, args=(world, _free_port(), name, True), nprocs=world, join=True)

@@ -21,10 +21,13 @@ def _install_fake_kernels():
         return orc.mask_from_slices(qr.tolist(), kr.tolist(), ty.tolist(), tq, tk)
 
     def fake_fwd(q, k, v, sink, sink_layout, out, lse, qr, kr, ty, scale, softcap, out_type, **kw):
-        o, l = orc.attn_fwd(q.double(), k.double(), v.double(), _mask(qr, kr, ty, q.shape[0], k.shape[0]), scale)
+        mask = _mask(qr, kr, ty, q.shape[0], k.shape[0])
+        o, l = orc.attn_fwd(q.double(), k.double(), v.double(), mask, scale, sink=sink, sink_layout=sink_layout)
         mo, ml = orc.merge_out_lse(out.double(), lse.double(), o, l.double())
         out.copy_(mo)
         lse.copy_(ml)
+        if kw.get("return_max_logits"):
+            kw["max_logits"].copy_(torch.maximum(kw["max_logits"], orc.max_logits(q.double(), k.double(), mask, scale).float()))
         return out, None
 
     def _bwd(do, q, k, v, out, lse, qr, kr, ty, scale):
@@ -34,7 +37,9 @@ def _install_fake_kernels():
     def fake_bwd(do, q, k, v, sink, sink_layout, out, lse, dq, dk, dv, dsink, qr, kr, ty, scale, softcap, **kw):
         a, b, c = _bwd(do, q, k, v, out, lse, qr, kr, ty, scale)
         dq += a.to(dq.dtype); dk += b.to(dk.dtype); dv += c.to(dv.dtype)
-        return dq, dk, dv, None
+        if sink is not None:
+            dsink += orc.sink_bwd(sink, lse, out, do, sink_layout).to(dsink.dtype)
+        return dq, dk, dv, dsink
 
     def fake_lib_bwd(do, q, k, v, out, lse, dq, dk, dv, qr, kr, ty, scale, softcap=0.0, accumulate_dkv=False, sm_margin=0):
         a, b, c = _bwd(do, q, k, v, out, lse, qr, kr, ty, scale)
@@ -84,3 +89,45 @@ def _runtime_body(rank, world, name, degree):
 @pytest.mark.parametrize("name", ["causal", "sliding_window_causal", "sparse_attn_2k"])
 def test_cp_runtime_end_to_end_gloo(world, degree, name):
     _run(world, _runtime_body, name, degree)
+
+
+def _sink_body(rank, world, name, degree):
+    """Sink applied once (host stage), partial dsink per rank summed over the group, max_logits MAX-reduced."""
+    from magiattention_b200.api import calc_attn, compute_pad_size, dispatch, magi_attn_flex_key, undispatch
+    from magiattention_b200.common import AttnRanges
+    from magiattention_b200.config import DistAttnConfig, OverlapConfig
+
+    os.environ["MAGI_ATTENTION_DSINK_ALL_REDUCE_OP"] = "sum"
+    _install_fake_kernels()
+    cfg = next(c for c in mask_configs(4) if c["name"] == name)
+    T, H, HK, D, chunk = cfg["seqlen"], 2, 1, 8, 16
+    pad = compute_pad_size(T, world, chunk)
+    torch.manual_seed(33)
+    q, k, v, do = (torch.randn(T, h, D, dtype=torch.float64) for h in (H, HK, HK, H))
+    sink = torch.randn(3, H, dtype=torch.float64)
+    for x in (q, k, v, do, sink):
+        dist.broadcast(x, 0)
+    for x in (q, k, v, sink):
+        x.requires_grad_(True)
+    key = magi_attn_flex_key(AttnRanges.from_ranges(cfg["q_ranges"]), AttnRanges.from_ranges(cfg["k_ranges"]), cfg["types"], T, T,
+                             H, HK, D, pad, dist.group.WORLD,
+                             dist_attn_config=DistAttnConfig(overlap_config=OverlapConfig(True, degree)), chunk_size=chunk)
+    ol, meta = calc_attn(dispatch(q, key), dispatch(k, key), dispatch(v, key), key, sink=sink, return_max_logits=True)
+    out = undispatch(ol, key)
+    out.backward(do)
+    mask = orc.mask_from_slices(cfg["q_ranges"], cfg["k_ranges"], cfg["types"], T, T)
+    qd, kd, vd, sd = (x.detach() for x in (q, k, v, sink))
+    ro, rl = orc.attn_fwd(qd, kd, vd, mask, sink=sd, sink_layout="sh")
+    rdq, rdk, rdv = orc.attn_bwd(do, qd, kd, vd, ro, rl, mask)
+    torch.testing.assert_close(out.detach(), ro, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(undispatch(meta.lse, key).double(), rl.double(), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(meta.max_logits.double(), orc.max_logits(qd, kd, mask), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(q.grad, rdq, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(k.grad, rdk, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(v.grad, rdv, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(sink.grad, orc.sink_bwd(sd, rl, ro, do, "sh"), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("world,degree,name", [(2, 1, "causal"), (4, 2, "uncovered_rows")])
+def test_cp_runtime_sink_and_max_logits_gloo(world, degree, name):
+    _run(world, _sink_body, name, degree)

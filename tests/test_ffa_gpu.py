@@ -86,6 +86,116 @@ def test_ffa_head_dim_64(dtype):
     _run_case([], [], [], 130, 70, 2, 1, dtype, D=64)
 
 
+def _run_sink_case(qr, kr, ty, T, TK, HQ, HK, dtype, layout, s_sink, D=D, seed=3):
+    """fwd + bwd with an attention sink and return_max_logits against the oracle (same tolerance rule as _run_case)."""
+    from magiattention_b200.functional import flex_flash_attn_func
+
+    dev = _dev()
+    torch.manual_seed(seed)
+    q = torch.randn(T, HQ, D, dtype=dtype, device=dev, requires_grad=True)
+    k = torch.randn(TK, HK, D, dtype=dtype, device=dev, requires_grad=True)
+    v = torch.randn(TK, HK, D, dtype=dtype, device=dev, requires_grad=True)
+    do = torch.randn(T, HQ, D, dtype=dtype, device=dev)
+    sink = torch.randn((s_sink, HQ) if layout == "sh" else (T, s_sink, HQ), dtype=torch.float32, device=dev, requires_grad=True)
+    mk = lambda x, shape: torch.tensor(x, dtype=torch.int32, device=dev).reshape(shape)
+    out, meta = flex_flash_attn_func(q, k, v, mk(qr, (-1, 2)), mk(kr, (-1, 2)), mk(ty, (-1,)), sink=sink, sink_layout=layout,
+                                     return_max_logits=True)
+    mask = orc.mask_from_slices(qr, kr, ty, T, TK)
+    qc, kc, vc, doc, sc = (x.detach() for x in (q, k, v, do, sink))
+    ro64, rl = orc.attn_fwd(qc.double(), kc.double(), vc.double(), mask, sink=sc, sink_layout=layout)
+    lo, ll = orc.attn_fwd(qc, kc, vc, mask, high_precision=False, sink=sc, sink_layout=layout)
+    orc.check_close("out", out.detach(), ro64, lo, "out")
+    orc.check_close("lse", meta.lse, rl.float(), ll, "lse")
+    # max_logits: the kernel takes the max of fp32-accumulated 16-bit products, exactly what the fp64 oracle sees up to
+    # fp32 accumulation error
+    ml = orc.max_logits(qc.double(), kc.double(), mask)
+    assert meta.max_logits.dtype == torch.float32 and meta.max_logits.shape == (HQ,)
+    torch.testing.assert_close(meta.max_logits.double(), ml, atol=1e-4, rtol=1e-5)
+    out.backward(do)
+    ref = orc.attn_bwd(doc, qc.double(), kc.double(), vc.double(), ro64, rl.double(), mask)
+    lp = orc.attn_bwd(doc, qc, kc, vc, lo, ll, mask, high_precision=False)
+    for name, g, r, l in zip(("dq", "dk", "dv"), (q.grad, k.grad, v.grad), ref, lp):
+        orc.check_close(name, g, r, l, name, atol=orc.grad_atol(r))
+    ds_ref = orc.sink_bwd(sc, rl, ro64, doc, layout)
+    ds_lp = orc.sink_bwd(sc, ll, lo, doc, layout)  # from the low-precision forward: the reference's error yardstick
+    assert sink.grad is not None and sink.grad.dtype == torch.float32 and sink.grad.shape == sink.shape
+    # the reference's dsink thresholds (test_flex_flash_attn.py:1760-1768): few elements => coarse mismatch floor.
+    # "sh" dsink is a signed sum over all rows: an element that cancels to ~0 keeps the absolute error of its
+    # summands (16-bit rounding of `out` inside delta), so atol is relative to the largest element.
+    orc.check_close("dsink", sink.grad, ds_ref, ds_lp.float(), "dsink", atol=orc.dsink_atol(ds_ref),
+                    min_mismatch=max(1.0 / max(ds_ref.numel(), 1), 8e-2), norm_floor=0.015)
+
+
+@pytest.mark.parametrize("layout,s_sink", [("sh", 1), ("sh", 8), ("ssh", 3)])
+def test_ffa_attention_sink_and_max_logits(layout, s_sink):
+    """Attention sink (reference test_flex_flash_attn.py:1176-1200: fp32 sink, s_sink 1..8, layouts sh / ssh) + dsink +
+    max_logits over mixed mask types, uncovered rows, ragged tails, GQA; d = 128 and d = 64."""
+    cfgs = {c["name"]: c for c in mask_configs(1)}
+    for name in ("all_types_aspects", "uncovered_rows"):
+        c = cfgs[name]
+        _run_sink_case(c["q_ranges"], c["k_ranges"], c["types"], c["seqlen"], c["seqlen"], 4, 2, torch.bfloat16, layout, s_sink)
+    _run_sink_case([[0, 77], [100, 333]], [[0, 50], [10, 50]], [0, 2], 333, 50, 2, 2, torch.float16, layout, s_sink, D=64)
+    _run_sink_case([], [], [], 130, 70, 2, 1, torch.bfloat16, layout, s_sink)  # sink only: out 0, lse = lse(sink), dsink 0
+
+
+def test_max_logits_accumulates_across_calls():
+    """A given max_logits buffer is max-reduced into (the CP runtime passes one buffer through every stage)."""
+    from magiattention_b200.functional.flex_flash_attn import _flex_flash_attn_forward
+
+    dev = _dev()
+    torch.manual_seed(5)
+    T, H = 512, 2
+    q, k, v = (torch.randn(T, H, D, dtype=torch.bfloat16, device=dev) for _ in range(3))
+    mk = lambda x: torch.tensor(x, dtype=torch.int32, device=dev)
+    buf = torch.full((H,), float("-inf"), device=dev)
+    parts = []
+    for kr in ([0, 200], [200, 512]):
+        _, m = _flex_flash_attn_forward(q, k, v, None, "sh", None, None, mk([[0, T]]), mk([kr]), mk([0]), D ** -0.5, 0.0, None,
+                                        return_max_logits=True, max_logits=buf)
+        assert m.max_logits is buf
+        parts.append(orc.max_logits(q.double(), k.double(), orc.mask_from_slices([[0, T]], [kr], [0], T, T)))
+    torch.testing.assert_close(buf.double(), torch.maximum(*parts), atol=1e-4, rtol=1e-5)
+    # negative maxima take the other branch of the ordered-int atomic
+    buf2 = torch.full((H,), float("-inf"), device=dev)
+    # (k = -q seen through a square bi-causal slice = the diagonal only: every visible logit is -|q_i|^2 * scale < 0)
+    _flex_flash_attn_forward(q, -q, v, None, "sh", None, None, mk([[0, 64]]), mk([[0, 64]]), mk([3]), D ** -0.5, 0.0, None,
+                             return_max_logits=True, max_logits=buf2)
+    ref = orc.max_logits(q.double(), -q.double(), orc.mask_from_slices([[0, 64]], [[0, 64]], [3], T, T))
+    assert (ref < 0).all()
+    torch.testing.assert_close(buf2.double(), ref, atol=1e-4, rtol=1e-5)
+
+
+def _random_slices(rng, T, TK, density):
+    """Area-disjoint random rectangles: a random grid over (q, k) whose cells are kept with probability `density`, each
+    with a random mask type — what the reference's random generator produces (test_flex_flash_attn.py:159-183)."""
+    def cuts(n):
+        m = int(rng.integers(1, 7))
+        c = sorted(set([0, n] + [int(x) for x in rng.integers(1, max(n, 2), size=m)]))
+        return [(a, b) for a, b in zip(c[:-1], c[1:]) if b > a]
+    qr, kr, ty = [], [], []
+    for (q0, q1) in cuts(T):
+        for (k0, k1) in cuts(TK):
+            if rng.random() < density:
+                qr.append([q0, q1]); kr.append([k0, k1]); ty.append(int(rng.integers(0, 4)))
+    return qr, kr, ty
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_ffa_random_slices_fuzz(seed):
+    """Seeded fuzz: random area-disjoint slices of all four types over ragged (tq, tk), random GQA ratio, head_dim and
+    dtype, fwd + bwd against the oracle (4 cases per seed)."""
+    import numpy as np
+
+    rng = np.random.default_rng(1234 + seed)
+    for _ in range(4):
+        T, TK = int(rng.integers(1, 1400)), int(rng.integers(1, 1400))
+        hq, hk = [(1, 1), (2, 1), (4, 2), (6, 2), (3, 3)][int(rng.integers(0, 5))]
+        d = (64, 128)[int(rng.integers(0, 2))]
+        dtype = (torch.bfloat16, torch.float16)[int(rng.integers(0, 2))]
+        qr, kr, ty = _random_slices(rng, T, TK, float(rng.uniform(0.3, 1.0)))
+        _run_case(qr, kr, ty, T, TK, hq, hk, dtype, seed=seed, D=d)
+
+
 def test_ffa_ragged_and_empty():
     # ragged sizes, an empty slice, tq not a tile multiple, tk < one block
     _run_case([[0, 77], [77, 77], [100, 333]], [[0, 50], [3, 9], [10, 50]], [0, 0, 2], 333, 50, 2, 2, torch.bfloat16)
@@ -96,7 +206,8 @@ def test_ffa_ragged_and_empty():
 def test_ffa_golden_masks_full_size():
     """The golden-fixture masks (pinned to the reference's ref_attn_func at d=16 on CPU) re-run on the GPU
     kernels at d=128 against the same oracle."""
-    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    files = sorted(f for f in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                   if not os.path.basename(f).startswith("sink_"))
     assert files
     for f in files[:6]:
         g = np.load(f)
@@ -180,8 +291,12 @@ def test_error_behaviour():
     r = torch.tensor([[0, 64]], dtype=torch.int32, device=dev)
     with pytest.raises(AssertionError):
         flex_flash_attn_func(q, q, q, r, r, None, softcap=1.0)
-    with pytest.raises(AssertionError):
-        flex_flash_attn_func(q, q, q, r, r, None, sink=torch.zeros(1, 2, device=dev))
+    with pytest.raises(NotImplementedError):
+        flex_flash_attn_func(q, q, q, r, r, None, sink=torch.zeros(1, 2, D, device=dev), sink_layout="shd")
+    with pytest.raises(RuntimeError):  # more sink tokens than the kernel supports (reference: kMaxSeqlenSink = 8)
+        flex_flash_attn_func(q, q, q, r, r, None, sink=torch.zeros(9, 2, device=dev))
+    with pytest.raises(RuntimeError):  # sink must be fp32 [s_sink, hq]
+        flex_flash_attn_func(q, q, q, r, r, None, sink=torch.zeros(1, 3, device=dev))
     with pytest.raises(RuntimeError):
         q96 = torch.randn(64, 2, 96, dtype=torch.bfloat16, device=dev)
         flex_flash_attn_func(q96, q96, q96, r, r, None)

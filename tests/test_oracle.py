@@ -11,7 +11,9 @@ import torch
 from oracle import ffa_oracle as orc
 from mask_configs import mask_configs
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+_ALL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = [p for p in _ALL if not os.path.basename(p).startswith("sink_")]
+GOLDEN_SINK = [p for p in _ALL if os.path.basename(p).startswith("sink_")]
 
 
 def _bf16(a):
@@ -45,6 +47,29 @@ def test_oracle_matches_reference_golden(path):
     torch.testing.assert_close(out_lp.float(), torch.from_numpy(g["out_lp"]), atol=2e-2, rtol=2e-2)
     fin = ~torch.isinf(lse_lp)
     torch.testing.assert_close(lse_lp[fin], torch.from_numpy(g["lse_lp"])[fin], atol=1e-5, rtol=1e-5)
+
+
+def test_sink_golden_present():
+    assert len(GOLDEN_SINK) >= 5
+
+
+@pytest.mark.parametrize("path", GOLDEN_SINK, ids=[os.path.basename(p)[:-4] for p in GOLDEN_SINK])
+def test_oracle_sink_and_max_logits_match_reference_golden(path):
+    """Attention sink ("sh" and "ssh"), dsink and max_logits of the oracle against the reference's ref_attn_func
+    (fixtures: gen_golden.py main_sink)."""
+    g = np.load(path)
+    q, k, v, do = (_bf16(g[n]).double() for n in ("q", "k", "v", "do"))
+    sink, layout = torch.from_numpy(g["sink"]).double(), str(g["sink_layout"])
+    mask = orc.mask_from_slices(g["q_ranges"].tolist(), g["k_ranges"].tolist(), g["types"].tolist(), q.shape[0], k.shape[0])
+    out, lse = orc.attn_fwd(q, k, v, mask, sink=sink, sink_layout=layout)
+    assert not torch.isinf(lse).any()  # every row sees at least the sink
+    torch.testing.assert_close(lse.double(), torch.from_numpy(g["lse"]), atol=1e-10, rtol=1e-10)
+    torch.testing.assert_close(out, torch.from_numpy(g["out"]), atol=1e-10, rtol=1e-10)
+    dq, dk, dv = orc.attn_bwd(do, q, k, v, out, lse, mask)
+    for name, x in (("dq", dq), ("dk", dk), ("dv", dv)):
+        torch.testing.assert_close(x, torch.from_numpy(g[name]), atol=1e-9, rtol=1e-9)
+    torch.testing.assert_close(orc.sink_bwd(sink, lse, out, do, layout), torch.from_numpy(g["dsink"]), atol=1e-9, rtol=1e-9)
+    torch.testing.assert_close(orc.max_logits(q, k, mask), torch.from_numpy(g["max_logits"]), atol=1e-10, rtol=1e-10)
 
 
 def test_slice_mask_known_answers():
