@@ -20,5 +20,15 @@ from .magi_attn_interface import (  # noqa: F401
     magi_attn_flex_key,
     magi_attn_varlen_dispatch,
     magi_attn_varlen_key,
+    make_flex_key_for_new_mask_after_dispatch,
+    make_varlen_key_for_new_mask_after_dispatch,
     undispatch,
 )
+# data structures, types and config classes used in the API signatures (reference api/__init__.py __all__)
+from ..common.enum import AttnMaskType, AttnOverlapMode  # noqa: F401,E402
+from ..common.forward_meta import AttnForwardMeta  # noqa: F401,E402
+from ..common.ranges import AttnRanges  # noqa: F401,E402
+from ..config import DispatchConfig, DistAttnConfig, OverlapConfig  # noqa: F401,E402
+from ..dist_attn_runtime_mgr import DistAttnRuntimeKey  # noqa: F401,E402
+
+GeneralAttnMaskType = str | AttnMaskType | list  # str | AttnMaskType | list of either

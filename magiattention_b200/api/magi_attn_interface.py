@@ -12,16 +12,18 @@ import torch.distributed as dist
 
 from ..common.forward_meta import AttnForwardMeta
 from ..common.ranges import AttnRanges
-from ..config import DistAttnConfig
+from ..config import DispatchConfig, DistAttnConfig, OverlapConfig  # noqa: F401
 from ..dist_attn_runtime_mgr import (DistAttnRuntimeKey, DistAttnRuntimeMgr, init_dist_attn_runtime_key,
                                      init_dist_attn_runtime_mgr)
 from .functools import infer_attn_mask_from_cu_seqlens
 
 __all__ = ["magi_attn_varlen_key", "magi_attn_flex_key", "magi_attn_varlen_dispatch", "magi_attn_flex_dispatch", "dispatch",
-           "undispatch", "calc_attn", "get_position_ids", "get_most_recent_key", "clear_cache", "get_runtime_mgr"]
+           "undispatch", "calc_attn", "get_position_ids", "get_most_recent_key", "clear_cache", "get_runtime_mgr",
+           "make_flex_key_for_new_mask_after_dispatch", "make_varlen_key_for_new_mask_after_dispatch"]
 
 _MAX_CACHE = 100
 _mgr_cache: "OrderedDict[DistAttnRuntimeKey, DistAttnRuntimeMgr]" = OrderedDict()
+_groups: dict[int, dist.ProcessGroup | None] = {0: None}  # cp_group_id -> group (keys only carry the id)
 DEFAULT_CHUNK_SIZE = 2048
 
 
@@ -48,6 +50,11 @@ def magi_attn_flex_key(q_ranges: AttnRanges, k_ranges: AttnRanges, attn_mask_typ
         "use compute_pad_size(total_seqlen_q, cp_size, chunk_size)")
     key = init_dist_attn_runtime_key(q_ranges, k_ranges, attn_mask_type, total_seqlen_q, total_seqlen_k, pad_size, cs, group,
                                      num_heads_q, num_heads_kv, head_dim, dist_attn_config)
+    _groups[key.cp_group_id] = group
+    return _register(key, group)
+
+
+def _register(key: DistAttnRuntimeKey, group) -> DistAttnRuntimeKey:
     if key in _mgr_cache:
         _mgr_cache.move_to_end(key)
     else:
@@ -117,3 +124,34 @@ def get_most_recent_key(cp_group: dist.ProcessGroup | None = None) -> DistAttnRu
 
 def clear_cache(cp_group: dist.ProcessGroup | None = None) -> None:
     _mgr_cache.clear()
+
+
+def make_flex_key_for_new_mask_after_dispatch(q_ranges: AttnRanges, k_ranges: AttnRanges, attn_mask_type,
+                                              key_for_dispatch: DistAttnRuntimeKey, num_heads_q: int | None = None,
+                                              num_heads_kv: int | None = None, head_dim: int | None = None,
+                                              dist_attn_config: DistAttnConfig | None = None) -> DistAttnRuntimeKey:
+    """A key for a SECOND mask (hybrid-attention models) that reuses the dispatch solution of ``key_for_dispatch``: tensors
+    dispatched with the old key can be fed to ``calc_attn`` with the new one; kernel slices, transfer tables and overlap
+    stages are planned for the new mask (reference :1315-1530).  Only the overlap part of ``dist_attn_config`` applies."""
+    mgr = _mgr_cache.get(key_for_dispatch)
+    if mgr is None:
+        raise ValueError("The dist attn runtime key for dispatch does not exist!")
+    kd = key_for_dispatch
+    cfg = kd.config if dist_attn_config is None else DistAttnConfig(
+        dispatch_config=kd.config.dispatch_config, overlap_config=dist_attn_config.overlap_config,
+        high_precision_reduce=dist_attn_config.high_precision_reduce)
+    group = _groups[kd.cp_group_id]
+    dmask = kd.dispatch_mask or (kd.q_ranges, kd.k_ranges, kd.attn_mask_type)
+    key = init_dist_attn_runtime_key(q_ranges, k_ranges, attn_mask_type, kd.total_seqlen_q, kd.total_seqlen_k, kd.pad_size,
+                                     kd.chunk_size, group, num_heads_q or kd.num_heads_q, num_heads_kv or kd.num_heads_kv,
+                                     head_dim or kd.head_dim, cfg, dispatch_mask=dmask)
+    return _register(key, group)
+
+
+def make_varlen_key_for_new_mask_after_dispatch(cu_seqlens_q: torch.Tensor, cu_seqlens_k: torch.Tensor,
+                                                key_for_dispatch: DistAttnRuntimeKey, causal: bool = False,
+                                                window_size: tuple[int, int] = (-1, -1),
+                                                dist_attn_config: DistAttnConfig | None = None) -> DistAttnRuntimeKey:
+    """flash-attn-varlen flavour of :func:`make_flex_key_for_new_mask_after_dispatch` (reference :1167-1312)."""
+    qr, kr, ty, _, _ = infer_attn_mask_from_cu_seqlens(cu_seqlens_q, cu_seqlens_k, causal, window_size)
+    return make_flex_key_for_new_mask_after_dispatch(qr, kr, ty, key_for_dispatch, dist_attn_config=dist_attn_config)

@@ -39,6 +39,9 @@ class DistAttnRuntimeKey:
     cp_group_id: int
     cp_size: int
     config: DistAttnConfig
+    # (q_ranges, k_ranges, types) of the mask whose dispatch solution this key reuses; None = its own mask
+    # (reference: make_*_key_for_new_mask_after_dispatch pass ref_dispatch_meta_q/k, magi_attn_interface.py:1476-1530)
+    dispatch_mask: tuple | None = None
 
 
 def _mask_type_to_int(t) -> int:
@@ -52,7 +55,8 @@ def _mask_type_to_int(t) -> int:
 def init_dist_attn_runtime_key(q_ranges: AttnRanges, k_ranges: AttnRanges, attn_mask_type, total_seqlen_q: int,
                                total_seqlen_k: int, pad_size: int, chunk_size: int, cp_group: dist.ProcessGroup | None,
                                num_heads_q: int, num_heads_kv: int, head_dim: int,
-                               dist_attn_config: DistAttnConfig = DistAttnConfig()) -> DistAttnRuntimeKey:
+                               dist_attn_config: DistAttnConfig = DistAttnConfig(),
+                               dispatch_mask: tuple | None = None) -> DistAttnRuntimeKey:
     n = len(q_ranges)
     if not isinstance(attn_mask_type, (list, tuple)):
         attn_mask_type = [attn_mask_type] * n
@@ -61,7 +65,7 @@ def init_dist_attn_runtime_key(q_ranges: AttnRanges, k_ranges: AttnRanges, attn_
     cp_size = 1 if cp_group is None else dist.get_world_size(cp_group)
     return DistAttnRuntimeKey(tuple(q_ranges.to_naive_ranges()), tuple(k_ranges.to_naive_ranges()), types,
                               total_seqlen_q, total_seqlen_k, pad_size, chunk_size, num_heads_q, num_heads_kv, head_dim,
-                              id(cp_group) if cp_group is not None else 0, cp_size, dist_attn_config)
+                              id(cp_group) if cp_group is not None else 0, cp_size, dist_attn_config, dispatch_mask)
 
 
 class DistAttnRuntimeMgr:
@@ -75,7 +79,11 @@ class DistAttnRuntimeMgr:
         self.total_seqlen = total
         slices = [(q[0], q[1], k[0], k[1], t) for q, k, t in zip(key.q_ranges, key.k_ranges, key.attn_mask_type)
                   if q[1] > q[0] and k[1] > k[0]]
-        self.dispatch_meta: DispatchMeta = make_dispatch_meta(slices, total, key.chunk_size, self.cp_size)
+        dslices = slices
+        if key.dispatch_mask is not None:  # a second mask riding on another mask's dispatch solution
+            dq, dk, dt = key.dispatch_mask
+            dslices = [(q[0], q[1], k[0], k[1], t) for q, k, t in zip(dq, dk, dt) if q[1] > q[0] and k[1] > k[0]]
+        self.dispatch_meta: DispatchMeta = make_dispatch_meta(dslices, total, key.chunk_size, self.cp_size)
         ov = key.config.overlap_config
         degree = (ov.degree or 1) if ov.enable else 1
         if self.cp_size == 1:

@@ -131,3 +131,48 @@ def _sink_body(rank, world, name, degree):
 @pytest.mark.parametrize("world,degree,name", [(2, 1, "causal"), (4, 2, "uncovered_rows")])
 def test_cp_runtime_sink_and_max_logits_gloo(world, degree, name):
     _run(world, _sink_body, name, degree)
+
+
+def _new_mask_body(rank, world, degree):
+    """Hybrid attention: dispatch once with the causal key, then run a sliding-window mask and a block-sparse mask on the
+    SAME local shards through make_flex_key_for_new_mask_after_dispatch (reference api/magi_attn_interface.py:1315-1530)."""
+    from magiattention_b200.api import (calc_attn, compute_pad_size, dispatch, get_position_ids, magi_attn_flex_key,
+                                        make_flex_key_for_new_mask_after_dispatch, undispatch)
+    from magiattention_b200.common import AttnRanges
+    from magiattention_b200.config import DistAttnConfig, OverlapConfig
+
+    _install_fake_kernels()
+    cfgs = {c["name"]: c for c in mask_configs(4)}
+    base = cfgs["causal"]
+    T, H, HK, D, chunk = base["seqlen"], 2, 1, 8, 16
+    pad = compute_pad_size(T, world, chunk)
+    torch.manual_seed(5)
+    q, k, v, do = (torch.randn(T, h, D, dtype=torch.float64) for h in (H, HK, HK, H))
+    for x in (q, k, v, do):
+        dist.broadcast(x, 0)
+    key0 = magi_attn_flex_key(AttnRanges.from_ranges(base["q_ranges"]), AttnRanges.from_ranges(base["k_ranges"]), base["types"],
+                              T, T, H, HK, D, pad, dist.group.WORLD,
+                              dist_attn_config=DistAttnConfig(overlap_config=OverlapConfig(True, degree)), chunk_size=chunk)
+    ql, kl, vl = (dispatch(x, key0).requires_grad_(True) for x in (q, k, v))
+    for name in ("sliding_window_causal", "sparse_attn_2k"):
+        cfg = cfgs[name]
+        assert cfg["seqlen"] == T
+        key1 = make_flex_key_for_new_mask_after_dispatch(AttnRanges.from_ranges(cfg["q_ranges"]),
+                                                         AttnRanges.from_ranges(cfg["k_ranges"]), cfg["types"], key0)
+        assert key1 != key0 and torch.equal(get_position_ids(key1), get_position_ids(key0))  # same dispatch solution
+        ol, _ = calc_attn(ql, kl, vl, key1)
+        out = undispatch(ol, key1)
+        mask = orc.mask_from_slices(cfg["q_ranges"], cfg["k_ranges"], cfg["types"], T, T)
+        ro, rl = orc.attn_fwd(q, k, v, mask)
+        torch.testing.assert_close(out.detach(), ro, atol=1e-5, rtol=1e-5)
+        for x in (ql, kl, vl):
+            x.grad = None
+        out.backward(do)
+        rdq, rdk, rdv = orc.attn_bwd(do, q, k, v, ro, rl, mask)
+        for g, r in ((ql.grad, rdq), (kl.grad, rdk), (vl.grad, rdv)):
+            torch.testing.assert_close(undispatch(g, key0), r, atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("world,degree", [(2, 1), (4, 2)])
+def test_new_mask_after_dispatch_gloo(world, degree):
+    _run(world, _new_mask_body, degree)
