@@ -78,7 +78,8 @@ int make_map_f32_acc(CUtensorMap* m, void* ptr, int head_dim, int tokens, int he
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// forward kernel variant: 64 (default: 64-column kv blocks, double-buffered S) or 128 (B200_FFA_FWD_VARIANT=128)
+// forward kernel variant: 128 (default: 128-column kv blocks, ffa_fwd.cu) or 64 (B200_FFA_FWD_VARIANT=64: 64-column kv blocks
+// with a double-buffered S, ffa_fwd64.cu — measured slower, head_dim 128 only, no max_logits)
 int fwd_variant() {
   static int v = -1;
   if (v < 0) {
@@ -154,7 +155,8 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   if (int rc = make_map_thd(&tmQ, p->q, p->dtype, p->head_dim, p->total_q, p->num_heads_q, p->q_stride_t, p->q_stride_h, 128, "q")) return rc;
   // k/v may legally be empty (total_k == 0): point the maps at q so encoding succeeds; no block is ever loaded.
   const bool kv_empty = p->total_k == 0;
-  const int kv_box_rows = (fwd_variant() == 64 && p->head_dim == 128 && !p->max_logits) ? 64 : 128;
+  const bool use_fwd64 = fwd_variant() == 64 && p->head_dim == 128 && !p->max_logits;
+  const int kv_box_rows = use_fwd64 ? 64 : 128;
   if (int rc = make_map_thd(&tmK, kv_empty ? p->q : p->k, p->dtype, p->head_dim, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
                             kv_empty ? p->q_stride_t : p->k_stride_t, kv_empty ? p->q_stride_h : p->k_stride_h, kv_box_rows, "k")) return rc;
   if (int rc = make_map_thd(&tmV, kv_empty ? p->q : p->v, p->dtype, p->head_dim, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
@@ -177,8 +179,7 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   a.scale = p->softmax_scale;
   a.accumulate = p->accumulate;
   a.max_logits = p->max_logits;
-  // the 64-column experimental variant exists for head_dim 128 only and does not track max_logits
-  e = (fwd_variant() == 64 && p->head_dim == 128 && !p->max_logits)
+  e = use_fwd64
           ? ffa::launch_fwd64(p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream)
           : ffa::launch_fwd(p->head_dim, p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream);
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "fwd launch: %s", cudaGetErrorString(e));

@@ -138,6 +138,49 @@ def test_ffa_attention_sink_and_max_logits(layout, s_sink):
     _run_sink_case([], [], [], 130, 70, 2, 1, torch.bfloat16, layout, s_sink)  # sink only: out 0, lse = lse(sink), dsink 0
 
 
+def test_sink_then_accumulate_stages():
+    """CP stage order on one device: the host stage applies the sink, later stages merge their partial results into the
+    same fp32 accumulators (dist_attn.py:1278-1297); backward per stage against the global (out, lse), dsink from the
+    host stage only.  Must equal one-shot attention over the union of the key sets with the sink."""
+    from magiattention_b200.functional.flex_flash_attn import _flex_flash_attn_backward, _flex_flash_attn_forward
+
+    dev = _dev()
+    torch.manual_seed(9)
+    T, HQ, HK = 640, 4, 2
+    q, do = (torch.randn(T, HQ, D, dtype=torch.bfloat16, device=dev) for _ in range(2))
+    k, v = (torch.randn(T, HK, D, dtype=torch.bfloat16, device=dev) for _ in range(2))
+    sink = torch.randn(5, HQ, dtype=torch.float32, device=dev)
+    mk = lambda x, shape: torch.tensor(x, dtype=torch.int32, device=dev).reshape(shape)
+    stages = [([[0, 640]], [[0, 256]], [0]), ([[100, 640]], [[256, 400]], [2]), ([[0, 500]], [[400, 640]], [1])]
+    out = torch.zeros(T, HQ, D, dtype=torch.float32, device=dev)
+    lse = torch.full((T, HQ), float("-inf"), dtype=torch.float32, device=dev)
+    for i, (qr, kr, ty) in enumerate(stages):
+        _flex_flash_attn_forward(q, k, v, sink if i == 0 else None, "sh", out, lse, mk(qr, (-1, 2)), mk(kr, (-1, 2)), mk(ty, (-1,)),
+                                 D ** -0.5, 0.0, torch.float32)
+    qr_all, kr_all, ty_all = (sum((s[i] for s in stages), []) for i in range(3))
+    mask = orc.mask_from_slices(qr_all, kr_all, ty_all, T, T)
+    ro, rl = orc.attn_fwd(q.double(), k.double(), v.double(), mask, sink=sink)
+    lo, ll = orc.attn_fwd(q, k, v, mask, high_precision=False, sink=sink)
+    orc.check_close("out", out, ro, lo, "out")
+    orc.check_close("lse", lse, rl.float(), ll, "lse")
+    out16 = out.to(q.dtype)
+    dq = torch.zeros(T, HQ, D, dtype=torch.float32, device=dev)
+    dk, dv = (torch.zeros(T, HK, D, dtype=torch.float32, device=dev) for _ in range(2))
+    dsink = None
+    for i, (qr, kr, ty) in enumerate(stages):
+        _, _, _, ds = _flex_flash_attn_backward(do, q, k, v, sink if i == 0 else None, "sh", out16, lse, dq, dk, dv, None,
+                                                mk(qr, (-1, 2)), mk(kr, (-1, 2)), mk(ty, (-1,)), D ** -0.5, 0.0)
+        dsink = ds if i == 0 else dsink
+        assert (ds is None) == (i != 0)
+    ref = orc.attn_bwd(do, q.double(), k.double(), v.double(), ro, rl.double(), mask)
+    lp = orc.attn_bwd(do, q, k, v, lo, ll, mask, high_precision=False)
+    for name, g, r, l in zip(("dq", "dk", "dv"), (dq, dk, dv), ref, lp):
+        orc.check_close(name, g, r, l, name, atol=orc.grad_atol(r))
+    ds_ref, ds_lp = orc.sink_bwd(sink, rl, ro, do), orc.sink_bwd(sink, ll, lo, do)
+    orc.check_close("dsink", dsink, ds_ref, ds_lp.float(), "dsink", atol=orc.dsink_atol(ds_ref),
+                    min_mismatch=max(1.0 / ds_ref.numel(), 8e-2), norm_floor=0.015)
+
+
 def test_max_logits_accumulates_across_calls():
     """A given max_logits buffer is max-reduced into (the CP runtime passes one buffer through every stage)."""
     from magiattention_b200.functional.flex_flash_attn import _flex_flash_attn_forward

@@ -16,4 +16,6 @@ tail -3 gpurun_out/ncu_full.err
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k 'regex:ffa_(fwd|bwd)_kernel' -c 2 \
     --csv --log-file gpurun_out/traffic_256k.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/bench_ncu_traffic.json 2> gpurun_out/ncu_traffic.err
 tail -3 gpurun_out/ncu_traffic.err
+timeout 300 python tools/dev/c2_bench.py 2>&1 | tail -3 | tee gpurun_out/c2_like.txt
+timeout 300 python tools/dev/c2_bench.py --c5 2>&1 | tail -3 | tee gpurun_out/c5_like.txt
 ls -la gpurun_out
