@@ -12,3 +12,6 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
     config.addinivalue_line("markers", "slow: long-running case")
+    # no single test may hang the suite (pytest-timeout; multi-process tests additionally police their own children)
+    if config.pluginmanager.hasplugin("timeout") and not getattr(config.option, "timeout", None):
+        config.option.timeout = 900

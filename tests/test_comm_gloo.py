@@ -2,29 +2,21 @@
 naive world-level semantics, driven by the planner's real transfer tables, plus a full staged CP attention
 (forward merge + dKV reduction) where the per-stage attention math is done by the oracle."""
 import os
-import socket
 
 import pytest
 import torch
 import torch.distributed as dist
-import torch.multiprocessing as mp
 
+from mp_util import spawn_with_deadline
 from oracle import ffa_oracle as orc
-
-
-def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
 
 
 def _worker(rank, world, port, fn, args):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["MAGI_B200_ALLOW_HOST_COMM_TEST"] = "1"
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import datetime
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=120))
     try:
         fn(rank, world, *args)
         dist.barrier()  # nobody tears the group down while a peer still has traffic in flight
@@ -40,7 +32,7 @@ def _worker(rank, world, port, fn, args):
 
 
 def _run(world, fn, *args):
-    mp.spawn(_worker, args=(world, _free_port(), fn, args), nprocs=world, join=True)
+    spawn_with_deadline(_worker, world, (fn, args))
 
 
 def _plan(T, cp, chunk, degree, slices):

@@ -7,12 +7,12 @@
   undispatch / backward) against the global oracle.
 """
 import os
-import socket
 
 import pytest
 import torch
 
 from mask_configs import mask_configs
+from mp_util import spawn_with_deadline
 from oracle import ffa_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -106,11 +106,6 @@ def test_virtual_cp_real_kernels(name):
 
 
 # ---------------------------------------------------------------------------------------------------
-def _free_port():
-    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
-    return p
-
-
 def _cp_worker(rank, world, port, name, with_sink=False):
     import torch.distributed as dist
     from magiattention_b200.api import calc_attn, compute_pad_size, dispatch, magi_attn_flex_key, undispatch
@@ -119,7 +114,8 @@ def _cp_worker(rank, world, port, name, with_sink=False):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=180))
     try:
         cfg = next(c for c in mask_configs(1) if c["name"] == name)
         T, H, HK, chunk = cfg["seqlen"], 4, 2, 128
@@ -164,10 +160,8 @@ def _cp_worker(rank, world, port, name, with_sink=False):
 def test_real_cp_nccl(name):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    import torch.multiprocessing as mp
-
     world = min(torch.cuda.device_count(), 4)
-    mp.spawn(_cp_worker, args=(world, _free_port(), name), nprocs=world, join=True)
+    spawn_with_deadline(_cp_worker, world, (name,), deadline_s=300)
 
 
 @pytest.mark.parametrize("name", ["uncovered_rows", "all_types_aspects"])
@@ -177,7 +171,5 @@ def test_real_cp_nccl_sink_and_max_logits(name):
     cp = 1 on a single GPU (stage loop degenerate, same code path) and at cp = min(#GPUs, 4) otherwise."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    import torch.multiprocessing as mp
-
     world = min(torch.cuda.device_count(), 4)
-    mp.spawn(_cp_worker, args=(world, _free_port(), name, True), nprocs=world, join=True)
+    spawn_with_deadline(_cp_worker, world, (name, True), deadline_s=300)
