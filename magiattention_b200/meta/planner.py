@@ -181,8 +181,14 @@ class AttnArg:
     def can_skip(self) -> bool:
         return len(self.q_ranges) == 0
 
-    def to_ffa_args(self, device) -> dict[str, torch.Tensor]:
-        """int32 device tensors (cached) — reference AttnArg.to_ffa_args, calc_meta.py:146-159."""
+    def to_ffa_args(self, is_bwd=False, device=None) -> dict[str, torch.Tensor]:
+        """int32 device tensors (cached) — reference AttnArg.to_ffa_args(is_bwd), calc_meta.py:146-159,210-223.
+        Forward and backward use the same slice list here (the kernels build their own tile->slice plans), so ``is_bwd``
+        only exists for signature parity; a torch.device passed first is taken as ``device`` (default: current CUDA device)."""
+        if isinstance(is_bwd, (torch.device, str)):
+            device = is_bwd
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         key = str(device)
         if key not in self._dev:
             mk = lambda x, shape: torch.tensor(x, dtype=torch.int32, device=device).reshape(shape)
