@@ -41,6 +41,22 @@ def causal_area(s: int) -> int:
     return s * (s + 1) // 2
 
 
+def slices_area(q_ranges, k_ranges, types) -> int:
+    """Unmasked (q, k) pairs of a slice list (host lists): the algorithmic work of one kernel call."""
+    import numpy as np
+
+    total = 0
+    for (q0, q1), (k0, k1), t in zip(q_ranges, k_ranges, types):
+        sq, sk = q1 - q0, k1 - k0
+        if sq <= 0 or sk <= 0:
+            continue
+        i = np.arange(sq, dtype=np.int64)
+        lo = i if t & 2 else np.zeros_like(i)                    # inv-causal edge: j >= i
+        hi = i + (sk - sq) + 1 if t & 1 else np.full_like(i, sk)  # causal edge:     j <= i + sk - sq
+        total += int(np.clip(np.minimum(hi, sk) - np.maximum(lo, 0), 0, None).sum())
+    return total
+
+
 # --------------------------------------------------------------------------------------------------
 # clocks sampling (B200_PROFILING.md recipe)
 # --------------------------------------------------------------------------------------------------
@@ -186,8 +202,18 @@ def main():
     def cnt_fwd(*x, **k):
         n = orig_fwd(*x, **k); launches[0] += n; return n
 
+    probe: list | None = None  # when a list: (flops, start event, end event) of every backward call of one step
+
     def cnt_bwd(*x, **k):
-        n = orig_bwd(*x, **k); launches[0] += n; return n
+        if probe is None:
+            n = orig_bwd(*x, **k); launches[0] += n; return n
+        qr_, kr_, ty_ = x[9].tolist(), x[10].tolist(), (x[11].tolist() if x[11] is not None else [0] * x[9].shape[0])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = orig_bwd(*x, **k)
+        e1.record()
+        probe.append((2.5 * 4.0 * slices_area(qr_, kr_, ty_) * x[1].shape[1] * x[1].shape[2], e0, e1))
+        return n
 
     _lib.ffa_fwd, _lib.ffa_bwd = cnt_fwd, cnt_bwd
     orig_rr = _lib.range_reduce_sum
@@ -300,6 +326,27 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained",
                 "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read+write, profiles/traffic_256k.json)",
                 "fwd_kernel": {"achieved": flops_fwd(causal_area(S), H) / ms_f / 1e9, "ms": ms_f}, "ms": ms_b}
+    else:
+        # CP: one extra (untimed) step with every b200_ffa_bwd call of this rank bracketed by events on the compute stream;
+        # achieved = algorithmic FLOPs of those calls / their summed duration, while the stage exchange runs beside them
+        probe = []
+        step(q, k, v, do)
+        barrier()
+        calls, probe = probe, None
+        fl_b = sum(c[0] for c in calls)
+        ms_b = sum(c[1].elapsed_time(c[2]) for c in calls)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        ach = fl_b / max(ms_b, 1e-9) / 1e9
+        roof = {"bound": "tensor", "kernel": f"ffa_bwd_kernel (rank 0: {len(calls)} event-bracketed b200_ffa_bwd calls of one step, "
+                "host + remote stages, KV exchange running concurrently)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained",
+                "traffic": None, "ms": ms_b}
     if rank == 0:
         clocks = sampler.stop()
 

@@ -28,3 +28,14 @@ def test_reference_arm_nonzero_rank_is_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                         "--gpus", "2"], capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_slices_area_matches_oracle_mask_area():
+    """bench.py counts algorithmic FLOPs from closed-form slice areas; pin them to the oracle's dense masks."""
+    import bench
+    from mask_configs import mask_configs
+    from oracle import ffa_oracle as orc
+
+    for c in mask_configs(1):
+        assert bench.slices_area(c["q_ranges"], c["k_ranges"], c["types"]) == orc.mask_area(c["q_ranges"], c["k_ranges"], c["types"])
+    assert bench.slices_area([[0, 4096]], [[0, 4096]], [1]) == bench.causal_area(4096)
