@@ -102,6 +102,21 @@ def test_argument_validation_needs_no_gpu(lib):
     p.num_heads_kv, p.softcap = 2, 1.0
     assert lib.b200_ffa_fwd(C.byref(p), None) == -4
     assert lib.b200_ffa_fwd(None, None) == -1
+    # sink / scale validation (fake non-null pointers: rejected before anything is dereferenced or launched)
+    p.softcap, p.total_q, p.total_k, p.out_dtype = 0.0, 64, 64, _lib.B200_BF16
+    p.q = p.k = p.v = p.out = p.lse = p.sink = 0x1000
+    p.softmax_scale, p.seqlen_sink = 0.1, 9
+    assert lib.b200_ffa_fwd(C.byref(p), None) == -1 and b"seqlen_sink" in lib.b200_ffa_last_error()
+    p.seqlen_sink, p.sink_layout = 4, 2
+    assert lib.b200_ffa_fwd(C.byref(p), None) == -4 and b"sink_layout" in lib.b200_ffa_last_error()
+    p.sink_layout, p.softmax_scale = 0, 0.0
+    assert lib.b200_ffa_fwd(C.byref(p), None) == -1 and b"softmax_scale" in lib.b200_ffa_last_error()
+    b = _lib.BwdParams()
+    b.dtype, b.dkv_dtype, b.head_dim, b.num_heads_q, b.num_heads_kv = _lib.B200_BF16, _lib.B200_BF16, 64, 4, 2
+    b.total_q = b.total_k = 64
+    b.q = b.k = b.v = b.out = b.dout = b.lse = b.dq = b.dk = b.dv = b.sink = 0x1000
+    b.softmax_scale, b.seqlen_sink = 0.1, 2
+    assert lib.b200_ffa_bwd(C.byref(b), None) == -1 and b"dsink" in lib.b200_ffa_last_error()
 
 
 def test_product_path_has_no_host_fallback():
