@@ -1,1 +1,2 @@
-from magiattention_b200.config import DispatchConfig, DistAttnConfig, OverlapConfig  # noqa: F401
+from magiattention_b200.config import *  # noqa: F401,F403
+from magiattention_b200.config import __all__  # noqa: F401

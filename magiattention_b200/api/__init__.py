@@ -28,7 +28,11 @@ from .magi_attn_interface import (  # noqa: F401
 from ..common.enum import AttnMaskType, AttnOverlapMode  # noqa: F401,E402
 from ..common.forward_meta import AttnForwardMeta  # noqa: F401,E402
 from ..common.ranges import AttnRanges  # noqa: F401,E402
-from ..config import DispatchConfig, DistAttnConfig, OverlapConfig  # noqa: F401,E402
+from ..config import (  # noqa: F401,E402
+    BSDispatchAlg, DispatchAlg, DispatchConfig, DistAttnConfig, DPDispatchAlg, GreedyOverlapAlg, GrpCollConfig, LBDispatchAlg,
+    MinHeapDispatchAlg, OverlapAlg, OverlapConfig, SequentialDispatchAlg, SortedSequentialSelectAlg, ToppHeapDispatchAlg,
+    UniformOverlapAlg,
+)
 from ..dist_attn_runtime_mgr import DistAttnRuntimeKey  # noqa: F401,E402
 
 GeneralAttnMaskType = str | AttnMaskType | list  # str | AttnMaskType | list of either

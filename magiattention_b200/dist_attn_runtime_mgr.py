@@ -83,11 +83,9 @@ class DistAttnRuntimeMgr:
         if key.dispatch_mask is not None:  # a second mask riding on another mask's dispatch solution
             dq, dk, dt = key.dispatch_mask
             dslices = [(q[0], q[1], k[0], k[1], t) for q, k, t in zip(dq, dk, dt) if q[1] > q[0] and k[1] > k[0]]
-        self.dispatch_meta: DispatchMeta = make_dispatch_meta(dslices, total, key.chunk_size, self.cp_size)
-        ov = key.config.overlap_config
-        degree = (ov.degree or 1) if ov.enable else 1
-        if self.cp_size == 1:
-            degree = 1
+        self.dispatch_meta: DispatchMeta = make_dispatch_meta(dslices, total, key.chunk_size, self.cp_size,
+                                                              key.config.dispatch_config.planner_alg)
+        degree = key.config.overlap_config.num_stages(self.cp_size)
         comm_metas, calc_metas = make_attn_meta(slices, self.dispatch_meta, degree)
         self.comm_meta, self.calc_meta = comm_metas[self.cp_rank], calc_metas[self.cp_rank]
         self.all_calc_metas = calc_metas  # kept for FLOP / balance accounting

@@ -134,11 +134,15 @@ class DispatchMeta:
 
 
 def make_dispatch_meta(slices: list[tuple[int, int, int, int, int]], total_seqlen: int, chunk_size: int,
-                       cp_size: int) -> DispatchMeta:
-    """Min-heap area balancing with an equal chunk count per rank (reference default MinHeap dispatch,
-    meta/_make_dispatch_meta.py:221, meta/solver/dispatch_solver.py:149): chunks in decreasing mask area
-    go to the least-loaded rank that still has room."""
+                       cp_size: int, alg: str = "min_heap") -> DispatchMeta:
+    """Chunk -> rank assignment with an equal chunk count per rank.
+
+    ``min_heap`` (reference default, meta/_make_dispatch_meta.py:221, meta/solver/dispatch_solver.py:894-1000): chunks in
+    decreasing mask area go to the least-loaded rank that still has room.  ``sequential`` (:1178-1212): rank r owns the
+    r-th contiguous block of chunks (no balancing; what ring / Ulysses style CP would see).  ``sorted_sequential``
+    (SortedSequentialSelectAlg): area-sorted chunks dealt out in snake order 0..cp-1, cp-1..0, ..."""
     assert total_seqlen % (chunk_size * cp_size) == 0, "total_seqlen must be a multiple of chunk_size * cp_size"
+    assert alg in ("min_heap", "sequential", "sorted_sequential"), f"unknown dispatch algorithm {alg!r}"
     n_chunks = total_seqlen // chunk_size
     per_rank = n_chunks // cp_size
     areas = np.zeros(n_chunks, dtype=np.int64)
@@ -146,7 +150,16 @@ def make_dispatch_meta(slices: list[tuple[int, int, int, int, int]], total_seqle
         q0, q1 = s[0], s[1]
         for ch in range(q0 // chunk_size, (max(q1, q0 + 1) - 1) // chunk_size + 1):
             areas[ch] += slice_area(s, ch * chunk_size, (ch + 1) * chunk_size)
+    if alg == "sequential":
+        return DispatchMeta(total_seqlen, chunk_size, cp_size,
+                            [list(range(r * per_rank, (r + 1) * per_rank)) for r in range(cp_size)])
     order = sorted(range(n_chunks), key=lambda i: (-int(areas[i]), i))
+    if alg == "sorted_sequential":
+        snake: list[list[int]] = [[] for _ in range(cp_size)]
+        for i, ch in enumerate(order):
+            rnd, pos = divmod(i, cp_size)
+            snake[pos if rnd % 2 == 0 else cp_size - 1 - pos].append(ch)
+        return DispatchMeta(total_seqlen, chunk_size, cp_size, [sorted(p) for p in snake])
     heap = [(0, r) for r in range(cp_size)]
     heapq.heapify(heap)
     parts: list[list[int]] = [[] for _ in range(cp_size)]

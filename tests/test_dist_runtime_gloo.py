@@ -52,10 +52,10 @@ def _install_fake_kernels():
     _lib.ffa_bwd = fake_lib_bwd
 
 
-def _runtime_body(rank, world, name, degree):
+def _runtime_body(rank, world, name, degree, alg=None):
     from magiattention_b200.api import calc_attn, compute_pad_size, dispatch, magi_attn_flex_key, undispatch
     from magiattention_b200.common import AttnRanges
-    from magiattention_b200.config import DistAttnConfig, OverlapConfig
+    from magiattention_b200.config import DispatchConfig, DistAttnConfig, OverlapConfig
 
     _install_fake_kernels()
     cfg = next(c for c in mask_configs(4) if c["name"] == name)
@@ -68,7 +68,9 @@ def _runtime_body(rank, world, name, degree):
     q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
     key = magi_attn_flex_key(AttnRanges.from_ranges(cfg["q_ranges"]), AttnRanges.from_ranges(cfg["k_ranges"]), cfg["types"], T, T,
                              H, HK, D, pad, dist.group.WORLD,
-                             dist_attn_config=DistAttnConfig(overlap_config=OverlapConfig(True, degree)), chunk_size=chunk)
+                             dist_attn_config=DistAttnConfig(
+                                 dispatch_config=DispatchConfig(alg=alg) if alg is not None else DispatchConfig(),
+                                 overlap_config=OverlapConfig(True, degree)), chunk_size=chunk)
     ol, meta = calc_attn(dispatch(q, key), dispatch(k, key), dispatch(v, key), key)
     out = undispatch(ol, key)
     out.backward(do)
@@ -176,3 +178,13 @@ def _new_mask_body(rank, world, degree):
 @pytest.mark.parametrize("world,degree", [(2, 1), (4, 2)])
 def test_new_mask_after_dispatch_gloo(world, degree):
     _run(world, _new_mask_body, degree)
+
+
+@pytest.mark.parametrize("alg_name", ["sequential", "sorted_sequential"])
+def test_cp_runtime_other_dispatch_algorithms_gloo(alg_name):
+    """The runtime result does not depend on the dispatch solution: contiguous (ring-style) and snake dispatch, degree None
+    (planner-chosen stage count)."""
+    from magiattention_b200.config import SequentialDispatchAlg, SortedSequentialSelectAlg
+
+    alg = SequentialDispatchAlg() if alg_name == "sequential" else SortedSequentialSelectAlg()
+    _run(4, _runtime_body, "all_types_aspects", None, alg)

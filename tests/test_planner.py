@@ -208,3 +208,49 @@ def test_sliding_window_inference_bruteforce():
         for (a, b), (c, e) in zip(qr.to_naive_ranges(), kr.to_naive_ranges()):
             cover[a:b, c:e] += 1
         assert int(cover.max()) <= 1
+
+
+@pytest.mark.parametrize("alg", ["min_heap", "sequential", "sorted_sequential"])
+@pytest.mark.parametrize("cp", [2, 4])
+def test_dispatch_algorithms_partition_and_plan(alg, cp):
+    """Every dispatch algorithm yields a partition of the chunks with equal counts, and the CP plan built on it reproduces
+    the global mask (areas add up; simulated CP attention equals the oracle)."""
+    from magiattention_b200.meta.planner import make_attn_meta, make_dispatch_meta, slice_area
+
+    cfg = next(c for c in mask_configs(4) if c["name"] == "all_types_aspects")
+    sl = [(q[0], q[1], k[0], k[1], t) for q, k, t in zip(cfg["q_ranges"], cfg["k_ranges"], cfg["types"])]
+    chunk = 16
+    T = cfg["seqlen"] + (-cfg["seqlen"]) % (chunk * cp)
+    dm = make_dispatch_meta(sl, T, chunk, cp, alg)
+    flat = sorted(c for p in dm.partitions for c in p)
+    assert flat == list(range(T // chunk)) and len({len(p) for p in dm.partitions}) == 1
+    if alg == "sequential":
+        assert dm.partitions[0] == list(range(T // chunk // cp))
+    comm, calc = make_attn_meta(sl, dm, 2)
+    total = sum(c.local_attn_arg.total_area + sum(a.total_area for a in c.remote_attn_args_list) for c in calc)
+    assert total == sum(slice_area(s) for s in sl)
+    loads = [c.local_attn_arg.total_area + sum(a.total_area for a in c.remote_attn_args_list) for c in calc]
+    if alg != "sequential":  # the balancing algorithms keep the heaviest rank near the mean
+        assert max(loads) <= 1.35 * (sum(loads) / cp)
+
+
+def test_config_classes_match_reference_surface():
+    """Config objects as the reference's docs construct them (api/magi_attn_interface.py:1385-1395) are accepted and hashable."""
+    from magiattention_b200.common.enum import AttnOverlapMode
+    from magiattention_b200.config import (DispatchConfig, DistAttnConfig, GrpCollConfig, MinHeapDispatchAlg, OverlapConfig,
+                                           SequentialDispatchAlg, SortedSequentialSelectAlg, ToppHeapDispatchAlg, UniformOverlapAlg)
+
+    c = DistAttnConfig(dispatch_config=DispatchConfig(chunk_size=512, alg=MinHeapDispatchAlg()),
+                       overlap_config=OverlapConfig(enable=True, mode=AttnOverlapMode.STATIC, degree=2, min_chunk_size=512,
+                                                    max_num_chunks=64, alg=UniformOverlapAlg()),
+                       grpcoll_config=GrpCollConfig())
+    assert hash(c) == hash(DistAttnConfig(dispatch_config=DispatchConfig(chunk_size=512, alg=MinHeapDispatchAlg()),
+                                          overlap_config=OverlapConfig(True, 2)))
+    assert c.dispatch_config.planner_alg == "min_heap" and c.overlap_config.num_stages(8) == 2
+    assert DispatchConfig(alg=SequentialDispatchAlg()).planner_alg == "sequential"
+    assert DispatchConfig(alg=SortedSequentialSelectAlg()).planner_alg == "sorted_sequential"
+    assert DispatchConfig(alg=ToppHeapDispatchAlg(top_p=0.5)).planner_alg == "min_heap"
+    assert OverlapConfig(degree=0).num_stages(8) == 1 and OverlapConfig(degree=None).num_stages(8) == 4
+    assert OverlapConfig(degree=None).num_stages(2) == 2 and OverlapConfig(degree=3).num_stages(1) == 1
+    with pytest.raises(NotImplementedError):
+        DispatchConfig(uneven_shard=True)
