@@ -19,7 +19,7 @@ from .functools import infer_attn_mask_from_cu_seqlens
 
 __all__ = ["magi_attn_varlen_key", "magi_attn_flex_key", "magi_attn_varlen_dispatch", "magi_attn_flex_dispatch", "dispatch",
            "undispatch", "calc_attn", "get_position_ids", "get_most_recent_key", "clear_cache", "get_runtime_mgr",
-           "make_flex_key_for_new_mask_after_dispatch", "make_varlen_key_for_new_mask_after_dispatch"]
+           "make_flex_key_for_new_mask_after_dispatch", "make_varlen_key_for_new_mask_after_dispatch", "roll", "roll_simple"]
 
 _MAX_CACHE = 100
 _mgr_cache: "OrderedDict[DistAttnRuntimeKey, DistAttnRuntimeMgr]" = OrderedDict()
@@ -89,6 +89,17 @@ def dispatch(x: torch.Tensor, key: DistAttnRuntimeKey) -> torch.Tensor:
 def undispatch(x: torch.Tensor, key: DistAttnRuntimeKey) -> torch.Tensor:
     """This rank's shard -> global [total_seqlen, ...] (all-gather + unpermute + unpad)."""
     return get_runtime_mgr(key).undispatch_qo(x)
+
+
+def roll(x: torch.Tensor, shift: int, dim: int, key: DistAttnRuntimeKey) -> torch.Tensor:
+    """Cyclically roll a dispatched local tensor along ``dim`` of the GLOBAL (padded) sequence — multi-token-prediction
+    labels; equals undispatch -> torch.roll -> dispatch without materialising the global tensor (reference :960-1001)."""
+    return get_runtime_mgr(key).roll(x, shift, dim)
+
+
+def roll_simple(x: torch.Tensor, shift: int, dim: int, key: DistAttnRuntimeKey) -> torch.Tensor:
+    """:func:`roll` with plain isend / irecv instead of one grouped batch (reference :1004-1038)."""
+    return get_runtime_mgr(key).roll_simple(x, shift, dim)
 
 
 def magi_attn_flex_dispatch(x: torch.Tensor, *args, **kwargs) -> tuple[torch.Tensor, DistAttnRuntimeKey]:

@@ -19,6 +19,7 @@ from .common.ranges import AttnRanges
 from .config import DistAttnConfig
 from .functional.dist_attn import DistAttnRuntime, dist_attn_func
 from .functional.dispatch import dispatch_func, undispatch_func
+from .functional.roll import roll_func, roll_simple_func
 from .meta.planner import DispatchMeta, make_attn_meta, make_dispatch_meta
 
 __all__ = ["DistAttnRuntimeKey", "DistAttnRuntimeMgr", "init_dist_attn_runtime_key", "init_dist_attn_runtime_mgr"]
@@ -104,6 +105,13 @@ class DistAttnRuntimeMgr:
         return undispatch_func(x, self.dispatch_meta, self.cp_rank, self.cp_group, self.key.pad_size)
 
     undispatch_kv = undispatch_qo
+
+    def roll(self, x: torch.Tensor, shift: int, dim: int) -> torch.Tensor:
+        """Cyclic roll of a dispatched tensor along the global sequence (reference :200-221)."""
+        return roll_func(x, shift, self.dispatch_meta, self.cp_rank, self.cp_group, dim)
+
+    def roll_simple(self, x: torch.Tensor, shift: int, dim: int) -> torch.Tensor:
+        return roll_simple_func(x, shift, self.dispatch_meta, self.cp_rank, self.cp_group, dim)
 
     # ---- attention (reference :246-265) --------------------------------------------------------------
     def calc_attn(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, sink: torch.Tensor | None = None,

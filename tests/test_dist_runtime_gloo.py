@@ -188,3 +188,39 @@ def test_cp_runtime_other_dispatch_algorithms_gloo(alg_name):
 
     alg = SequentialDispatchAlg() if alg_name == "sequential" else SortedSequentialSelectAlg()
     _run(4, _runtime_body, "all_types_aspects", None, alg)
+
+
+def _roll_body(rank, world):
+    """roll / roll_simple == dispatch(torch.roll(undispatch(x))) incl. padding rows, any dim, autograd (= roll by -shift)."""
+    from magiattention_b200.api import compute_pad_size, dispatch, magi_attn_flex_key, roll, roll_simple, undispatch
+    from magiattention_b200.api.magi_attn_interface import get_runtime_mgr
+    from magiattention_b200.common import AttnRanges
+
+    T, chunk = 200, 16
+    pad = compute_pad_size(T, world, chunk)
+    key = magi_attn_flex_key(AttnRanges.from_ranges([[0, T]]), AttnRanges.from_ranges([[0, T]]), "causal", T, T, 2, 2, 8, pad,
+                             dist.group.WORLD, chunk_size=chunk)
+    mgr = get_runtime_mgr(key)
+    Tp = T + pad
+    torch.manual_seed(3)
+    g = torch.randn(Tp, 3, dtype=torch.float64)  # the padded global tensor as the dispatch sees it
+    dist.broadcast(g, 0)
+    pos = mgr.get_position_ids()
+    x = g[pos].clone().requires_grad_(True)
+    for fn in (roll, roll_simple):
+        for shift in (1, -1, 7, chunk, chunk + 3, -45, Tp, Tp + 2):
+            y = fn(x, shift, 0, key)
+            assert torch.equal(y.detach(), torch.roll(g, shift, 0)[pos]), (fn.__name__, shift)
+    # a non-leading sequence dim and the backward pass
+    xt = x.detach().t().contiguous().requires_grad_(True)  # [3, rows]
+    yt = roll(xt, 5, 1, key)
+    assert torch.equal(yt.detach(), torch.roll(g, 5, 0)[pos].t())
+    w = torch.randn(Tp, 3, dtype=torch.float64)
+    dist.broadcast(w, 0)
+    (yt * w[pos].t()).sum().backward()
+    assert torch.equal(xt.grad, torch.roll(w, -5, 0)[pos].t())
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_roll_gloo(world):
+    _run(world, _roll_body)
