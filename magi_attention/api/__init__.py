@@ -5,5 +5,6 @@ from magiattention_b200.api import (  # noqa: F401
     magi_attn_flex_dispatch, magi_attn_flex_key, magi_attn_varlen_dispatch, magi_attn_varlen_key, pad_at_dim,
     squash_batch_dim, undispatch, unpad_at_dim, make_flex_key_for_new_mask_after_dispatch,
     make_varlen_key_for_new_mask_after_dispatch, AttnForwardMeta, AttnMaskType, AttnOverlapMode, AttnRanges, DistAttnRuntimeKey,
-    GeneralAttnMaskType, DistAttnConfig, DispatchConfig, OverlapConfig, roll, roll_simple,
+    GeneralAttnMaskType, DistAttnConfig, DispatchConfig, OverlapConfig, roll, roll_simple, DistAttnRuntimeDictManager,
+    dist_attn_runtime_dict_mgr,
 )

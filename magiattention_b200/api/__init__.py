@@ -10,6 +10,8 @@ from .functools import (  # noqa: F401
     unpad_at_dim,
 )
 from .magi_attn_interface import (  # noqa: F401
+    DistAttnRuntimeDictManager,
+    dist_attn_runtime_dict_mgr,
     calc_attn,
     clear_cache,
     dispatch,

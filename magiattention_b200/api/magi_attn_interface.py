@@ -19,12 +19,43 @@ from .functools import infer_attn_mask_from_cu_seqlens
 
 __all__ = ["magi_attn_varlen_key", "magi_attn_flex_key", "magi_attn_varlen_dispatch", "magi_attn_flex_dispatch", "dispatch",
            "undispatch", "calc_attn", "get_position_ids", "get_most_recent_key", "clear_cache", "get_runtime_mgr",
-           "make_flex_key_for_new_mask_after_dispatch", "make_varlen_key_for_new_mask_after_dispatch", "roll", "roll_simple"]
+           "make_flex_key_for_new_mask_after_dispatch", "make_varlen_key_for_new_mask_after_dispatch", "roll", "roll_simple",
+           "DistAttnRuntimeDictManager", "dist_attn_runtime_dict_mgr"]
 
 _MAX_CACHE = 100
 _mgr_cache: "OrderedDict[DistAttnRuntimeKey, DistAttnRuntimeMgr]" = OrderedDict()
 _groups: dict[int, dist.ProcessGroup | None] = {0: None}  # cp_group_id -> group (keys only carry the id)
 DEFAULT_CHUNK_SIZE = 2048
+
+
+class DistAttnRuntimeDictManager:
+    """Dict-like view of the runtime-manager cache (reference :64-150): ``get`` / ``in`` / ``[]`` / ``keys`` /
+    ``get_most_recent_key`` / ``clear``.  One LRU of ``_MAX_CACHE`` entries serves every cp group here."""
+
+    def get(self, key: DistAttnRuntimeKey, default=None):
+        return _mgr_cache.get(key, default)
+
+    def __contains__(self, key: DistAttnRuntimeKey) -> bool:
+        return key in _mgr_cache
+
+    def __getitem__(self, key: DistAttnRuntimeKey) -> DistAttnRuntimeMgr:
+        return _mgr_cache[key]
+
+    def __setitem__(self, key: DistAttnRuntimeKey, value: DistAttnRuntimeMgr) -> None:
+        _mgr_cache[key] = value
+        _mgr_cache.move_to_end(key)
+
+    def keys(self, cp_group: dist.ProcessGroup | None = None):
+        return [k for k in _mgr_cache if cp_group is None or k.cp_group_id == id(cp_group)]
+
+    def get_most_recent_key(self, cp_group: dist.ProcessGroup | None = None) -> DistAttnRuntimeKey:
+        return get_most_recent_key(cp_group)
+
+    def clear(self, cp_group: dist.ProcessGroup | None = None) -> None:
+        clear_cache(cp_group)
+
+
+dist_attn_runtime_dict_mgr = DistAttnRuntimeDictManager()
 
 
 def _resolve_group(cp_group_or_mesh) -> dist.ProcessGroup | None:
@@ -128,13 +159,20 @@ def get_position_ids(key: DistAttnRuntimeKey) -> torch.Tensor:
 
 
 def get_most_recent_key(cp_group: dist.ProcessGroup | None = None) -> DistAttnRuntimeKey:
-    if not _mgr_cache:
-        raise ValueError("no dist attn runtime key has been created yet")
-    return next(reversed(_mgr_cache))
+    """The most recently created / used key (of ``cp_group`` when given) — reference :1136-1154."""
+    for k in reversed(_mgr_cache):
+        if cp_group is None or k.cp_group_id == id(cp_group):
+            return k
+    raise ValueError("no dist attn runtime key has been created yet")
 
 
 def clear_cache(cp_group: dist.ProcessGroup | None = None) -> None:
-    _mgr_cache.clear()
+    """Drop the cached runtime managers (of ``cp_group`` only when given) — reference :1157-1164."""
+    if cp_group is None:
+        _mgr_cache.clear()
+        return
+    for k in [k for k in _mgr_cache if k.cp_group_id == id(cp_group)]:
+        del _mgr_cache[k]
 
 
 def make_flex_key_for_new_mask_after_dispatch(q_ranges: AttnRanges, k_ranges: AttnRanges, attn_mask_type,

@@ -254,3 +254,16 @@ def test_config_classes_match_reference_surface():
     assert OverlapConfig(degree=None).num_stages(2) == 2 and OverlapConfig(degree=3).num_stages(1) == 1
     with pytest.raises(NotImplementedError):
         DispatchConfig(uneven_shard=True)
+
+
+# magi_attention/api/__init__.py __all__ of the reference (names only, snapshot taken by listing the module's __all__)
+REFERENCE_API_ALL = ['magi_attn_varlen_key', 'magi_attn_varlen_dispatch', 'magi_attn_flex_key', 'magi_attn_flex_dispatch', 'dispatch', 'undispatch', 'roll', 'roll_simple', 'calc_attn', 'clear_cache', 'get_most_recent_key', 'get_position_ids', 'make_varlen_key_for_new_mask_after_dispatch', 'make_flex_key_for_new_mask_after_dispatch', 'flex_flash_attn_func', 'compute_pad_size', 'squash_batch_dim', 'infer_varlen_mask_from_batch', 'infer_attn_mask_from_sliding_window', 'infer_attn_mask_from_cu_seqlens', 'AttnForwardMeta', 'AttnMaskType', 'AttnOverlapMode', 'AttnRanges', 'DistAttnRuntimeKey', 'GeneralAttnMaskType', 'DistAttnConfig', 'DispatchConfig', 'OverlapConfig', 'GrpCollConfig', 'DispatchAlg', 'MinHeapDispatchAlg', 'ToppHeapDispatchAlg', 'SequentialDispatchAlg', 'SortedSequentialSelectAlg', 'LBDispatchAlg', 'DPDispatchAlg', 'BSDispatchAlg', 'OverlapAlg', 'UniformOverlapAlg', 'GreedyOverlapAlg', 'DistAttnRuntimeDictManager', 'dist_attn_runtime_dict_mgr']
+
+
+def test_api_surface_covers_reference_all():
+    """Every public name of the reference's ``magi_attention.api`` resolves in the alias package and in our own package."""
+    import magi_attention.api as alias
+    import magiattention_b200.api as ours
+
+    missing = [n for n in REFERENCE_API_ALL if not hasattr(alias, n) or not hasattr(ours, n)]
+    assert not missing, missing
