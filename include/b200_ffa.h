@@ -16,6 +16,7 @@
  *                          (range_locks / tile semaphore flex_flash_fwd.hpp:299-318; softmax_d / lse_log2
  *                          flex_flash_bwd.hpp:351-352).  Here the CALLER owns the workspace.
  *   b200_lse_merge      <- correct_attn_out_lse (magi_attention/functional/utils.py:467-558, Triton).
+ *   b200_sink_merge     <- correct_attn_out_lse_with_sink (magi_attention/functional/utils.py:634-672).
  *   b200_range_reduce_sum <- range_reduce(sum) post-process of group_reduce
  *                          (magi_attention/common/range_op/_range_reduce.py:360).
  *
@@ -163,6 +164,15 @@ B200_API int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream);
  * out/out2: [rows, heads, dim] with the given dtypes (contiguous), lse/lse2: [rows, heads] fp32. */
 B200_API int b200_lse_merge(void* out, float* lse, const void* out2, const float* lse2, int64_t rows, int32_t heads,
                    int32_t dim, int32_t out_dtype, int32_t out2_dtype, b200_stream_t stream);
+
+/* In-place attention-sink merge of a finished (out, lse) pair — the sink pass of b200_ffa_fwd on its own:
+ *   lse' = logaddexp(lse, logsumexp_j sink_j); out' = out * exp(lse - lse').
+ * Replaces correct_attn_out_lse_with_sink (magi_attention/functional/utils.py:634-672).  out: [rows, heads, dim]
+ * (element strides given), lse: [rows, heads] fp32, sink fp32 with sink_layout 0 = "sh" [seqlen_sink, heads],
+ * 1 = "ssh" [rows, seqlen_sink, heads]; seqlen_sink <= 8. */
+B200_API int b200_sink_merge(void* out, float* lse, const float* sink, int64_t rows, int32_t heads, int32_t dim,
+                             int32_t seqlen_sink, int32_t sink_layout, int32_t out_dtype, int64_t o_stride_t, int64_t o_stride_h,
+                             int64_t lse_stride_t, int64_t lse_stride_h, b200_stream_t stream);
 
 /* dst[dst_ranges[i]] += src[src_ranges[i]] row-span by row-span (fp32 accumulate), row = `row_elems`
  * contiguous elements.  ranges are int32 [n,2] device arrays; spans i have equal length on both sides.

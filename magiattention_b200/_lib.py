@@ -71,7 +71,7 @@ class BwdParams(C.Structure):
 
 EXPORTS = [
     "b200_ffa_version", "b200_ffa_last_error", "b200_ffa_fwd_workspace_bytes", "b200_ffa_bwd_workspace_bytes",
-    "b200_ffa_fwd", "b200_ffa_bwd", "b200_lse_merge", "b200_range_reduce_sum", "b200_ffa_last_launch_count",
+    "b200_ffa_fwd", "b200_ffa_bwd", "b200_lse_merge", "b200_sink_merge", "b200_range_reduce_sum", "b200_ffa_last_launch_count",
 ]
 
 _lib = None
@@ -103,6 +103,9 @@ def lib() -> C.CDLL:
                 l.b200_lse_merge.restype = C.c_int
                 l.b200_lse_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                              C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+                l.b200_sink_merge.restype = C.c_int
+                l.b200_sink_merge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                              C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
                 l.b200_range_reduce_sum.restype = C.c_int
                 l.b200_range_reduce_sum.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                                     C.c_int32, C.c_int64, C.c_void_p]
@@ -264,6 +267,18 @@ def lse_merge(out: torch.Tensor, lse: torch.Tensor, out2: torch.Tensor, lse2: to
     rows, heads, dim = out.shape
     _check(l.b200_lse_merge(out.data_ptr(), lse.data_ptr(), out2.data_ptr(), lse2.data_ptr(), rows, heads, dim,
                             _DT[out.dtype], _DT[out2.dtype], _stream_ptr(out.device)), "b200_lse_merge")
+
+
+def sink_merge(out: torch.Tensor, lse: torch.Tensor, sink: torch.Tensor, sink_layout: str = "sh") -> None:
+    """(out, lse) <- merged with the attention sink, in place (out [rows, heads, dim] with contiguous dim, lse fp32)."""
+    l = lib()
+    _req(out, "out")
+    if lse.dtype != torch.float32 or lse.shape != out.shape[:2] or not lse.is_cuda:
+        raise RuntimeError("lse must be a CUDA fp32 [rows, heads] tensor")
+    ptr, s_sink, layout = _sink_args(sink, sink_layout, out.shape[0], out.shape[1], out.device)
+    _check(l.b200_sink_merge(out.data_ptr(), lse.data_ptr(), ptr, out.shape[0], out.shape[1], out.shape[2], s_sink, layout,
+                             _DT[out.dtype], out.stride(0), out.stride(1), lse.stride(0), lse.stride(1),
+                             _stream_ptr(out.device)), "b200_sink_merge")
 
 
 def range_reduce_sum(dst: torch.Tensor, src: torch.Tensor, dst_ranges: torch.Tensor, src_ranges: torch.Tensor) -> None:

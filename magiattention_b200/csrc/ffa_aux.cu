@@ -228,6 +228,18 @@ int b200_lse_merge(void* out, float* lse, const void* out2, const float* lse2, i
   });
 }
 
+int b200_sink_merge(void* out, float* lse, const float* sink, int64_t rows, int32_t heads, int32_t dim, int32_t seqlen_sink,
+                    int32_t sink_layout, int32_t out_dtype, int64_t o_stride_t, int64_t o_stride_h, int64_t lse_stride_t,
+                    int64_t lse_stride_h, b200_stream_t stream_) {
+  if (rows == 0 || heads == 0 || seqlen_sink == 0) return 0;
+  if (!out || !lse || !sink || rows < 0 || heads < 0 || dim <= 0) return B200_ERR_INVALID;
+  if (seqlen_sink < 0 || seqlen_sink > 8 || (sink_layout != 0 && sink_layout != 1)) return B200_ERR_INVALID;
+  if (out_dtype != B200_F16 && out_dtype != B200_BF16 && out_dtype != B200_F32) return B200_ERR_INVALID;
+  cudaError_t e = ffa::launch_sink_fwd(out_dtype, out, lse, sink, rows, heads, dim, seqlen_sink, sink_layout, o_stride_t, o_stride_h,
+                                       lse_stride_t, lse_stride_h, static_cast<cudaStream_t>(stream_));
+  return e == cudaSuccess ? int(B200_OK) : int(B200_ERR_CUDA);
+}
+
 int b200_range_reduce_sum(void* dst, int32_t dst_dtype, const void* src, int32_t src_dtype, const int32_t* dst_ranges,
                           const int32_t* src_ranges, int32_t num_ranges, int64_t row_elems, b200_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

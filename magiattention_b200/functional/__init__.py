@@ -7,3 +7,13 @@ from .flex_flash_attn import (  # noqa: F401
 )
 from .dist_attn import DistAttnFunc, DistAttnRuntime, dist_attn_func  # noqa: F401,E402
 from .dispatch import dispatch_func, undispatch_func  # noqa: F401,E402
+from .roll import roll_func, roll_simple_func  # noqa: F401,E402
+from .utils import (  # noqa: F401,E402
+    calc_lse_sink,
+    correct_attn_lse,
+    correct_attn_lse_with_sink,
+    correct_attn_out,
+    correct_attn_out_lse,
+    correct_attn_out_lse_with_sink,
+    correct_attn_out_with_sink,
+)

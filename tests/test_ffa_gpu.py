@@ -181,6 +181,34 @@ def test_sink_then_accumulate_stages():
                     min_mismatch=max(1.0 / ds_ref.numel(), 8e-2), norm_floor=0.015)
 
 
+def test_correct_attn_out_lse_kernels():
+    """functional.correct_attn_out_lse (b200_lse_merge) and correct_attn_out_lse_with_sink (b200_sink_merge) against the
+    oracle's merge, out of place and in place, bf16 and fp32 partials."""
+    from magiattention_b200.functional import correct_attn_out_lse, correct_attn_out_lse_with_sink
+
+    dev = _dev()
+    torch.manual_seed(2)
+    T, H = 300, 4
+    for dt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2)):
+        o1, o2 = (torch.randn(T, H, D, device=dev).to(dt) for _ in range(2))
+        l1, l2 = (torch.randn(T, H, device=dev) for _ in range(2))
+        l1[:7] = float("-inf"); o1[:7] = 0
+        l2[4:11] = float("-inf"); o2[4:11] = 0
+        ro, rl = orc.merge_out_lse(o1.double(), l1.double(), o2.double(), l2.double())
+        o, l = correct_attn_out_lse(o1, l1, o2, l2)
+        assert o.data_ptr() != o1.data_ptr() and torch.equal(torch.isinf(l), torch.isinf(rl))
+        torch.testing.assert_close(o.double(), ro, atol=tol, rtol=tol)
+        torch.testing.assert_close(l.double()[~torch.isinf(rl)], rl[~torch.isinf(rl)], atol=1e-5, rtol=1e-5)
+        for layout, sink in (("sh", torch.randn(3, H, device=dev)), ("ssh", torch.randn(T, 3, H, device=dev))):
+            ls = torch.logsumexp(orc._sink_hqs(sink.double(), T, layout), -1).t()
+            so, sl = orc.merge_out_lse(ro, rl, torch.zeros_like(ro), ls)
+            oc, lc = o.clone(), l.clone()
+            o3, l3 = correct_attn_out_lse_with_sink(oc, lc, sink, layout, inplace=True)
+            assert o3.data_ptr() == oc.data_ptr() and l3.data_ptr() == lc.data_ptr()
+            torch.testing.assert_close(o3.double(), so, atol=2 * tol, rtol=2 * tol)
+            torch.testing.assert_close(l3.double(), sl, atol=1e-5, rtol=1e-5)
+
+
 def test_max_logits_accumulates_across_calls():
     """A given max_logits buffer is max-reduced into (the CP runtime passes one buffer through every stage)."""
     from magiattention_b200.functional.flex_flash_attn import _flex_flash_attn_forward

@@ -129,3 +129,27 @@ def test_mask_configs_area_disjoint():
             assert 0 <= q0 <= q1 <= T and 0 <= k0 <= k1 <= T, cfg["name"]
             cover[q0:q1, k0:k1] += 1
         assert int(cover.max()) <= 1, cfg["name"]
+
+
+def test_correct_attn_helpers_match_oracle_merge():
+    """functional.utils torch-op helpers (correct_attn_lse / correct_attn_out / *_with_sink) against the oracle's merge and
+    sink restatements, incl. (-inf, -inf) rows."""
+    from magiattention_b200.functional.utils import (calc_lse_sink, correct_attn_lse, correct_attn_lse_with_sink, correct_attn_out,
+                                                     correct_attn_out_with_sink)
+
+    torch.manual_seed(0)
+    T, H, Dh = 50, 3, 8
+    o1, o2 = torch.randn(T, H, Dh, dtype=torch.float64), torch.randn(T, H, Dh, dtype=torch.float64)
+    l1, l2 = torch.randn(T, H, dtype=torch.float64), torch.randn(T, H, dtype=torch.float64)
+    l1[:5] = float("-inf"); o1[:5] = 0
+    l2[3:8] = float("-inf"); o2[3:8] = 0
+    ro, rl = orc.merge_out_lse(o1, l1, o2, l2)
+    lse = correct_attn_lse(l1, l2)
+    assert torch.equal(torch.isinf(lse), torch.isinf(rl))
+    torch.testing.assert_close(lse[~torch.isinf(rl)], rl[~torch.isinf(rl)])
+    torch.testing.assert_close(correct_attn_out(o1, l1, o2, l2, lse), ro)
+    for layout, sink in (("sh", torch.randn(4, H, dtype=torch.float64)), ("ssh", torch.randn(T, 4, H, dtype=torch.float64))):
+        ls = calc_lse_sink(sink, T, layout)
+        so, sl = orc.merge_out_lse(ro, rl, torch.zeros_like(ro), ls)
+        torch.testing.assert_close(correct_attn_lse_with_sink(rl, sink, layout), sl)
+        torch.testing.assert_close(correct_attn_out_with_sink(ro, rl, sink, layout), so)
