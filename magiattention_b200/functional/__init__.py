@@ -3,6 +3,7 @@ from .flex_flash_attn import (  # noqa: F401
     FlexFlashAttnFunc,
     _flex_flash_attn_backward,
     _flex_flash_attn_forward,
+    ffa_fa4_func,
     flex_flash_attn_func,
 )
 from .dist_attn import DistAttnFunc, DistAttnRuntime, dist_attn_func  # noqa: F401,E402

@@ -24,7 +24,7 @@ import torch
 from .. import _lib
 from ..common.forward_meta import AttnForwardMeta
 
-__all__ = ["flex_flash_attn_func", "_flex_flash_attn_forward", "_flex_flash_attn_backward", "FlexFlashAttnFunc"]
+__all__ = ["flex_flash_attn_func", "ffa_fa4_func", "_flex_flash_attn_forward", "_flex_flash_attn_backward", "FlexFlashAttnFunc"]
 
 
 def _maybe_contiguous(x: torch.Tensor | None) -> torch.Tensor | None:
@@ -219,3 +219,14 @@ def flex_flash_attn_func(
     out, lse, max_logits = FlexFlashAttnFunc.apply(
         q, k, v, sink, sink_layout, q_ranges, k_ranges, attn_type_map, softmax_scale, softcap, sm_margin, return_max_logits)
     return out, AttnForwardMeta(lse=lse, max_logits=max_logits)
+
+
+def ffa_fa4_func(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, q_ranges: torch.Tensor, k_ranges: torch.Tensor,
+                 attn_type_map: torch.Tensor | None = None, *, softmax_scale: float | None = None, softcap: float = 0.0,
+                 deterministic: bool = False, reuse_attn_arg: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
+    """The reference's B200 incumbent entry point (functional/fa4.py:421-470, used by exps/attn/run_blackwell_benchmark.py):
+    same kernels as :func:`flex_flash_attn_func`, returns ``(out, lse)``.  ``reuse_attn_arg`` has nothing to reuse here —
+    slices are consumed directly, there is no per-call mask conversion."""
+    out, meta = flex_flash_attn_func(q, k, v, q_ranges, k_ranges, attn_type_map, softmax_scale=softmax_scale, softcap=softcap,
+                                     deterministic=deterministic)
+    return out, meta.lse
