@@ -256,6 +256,30 @@ def test_config_classes_match_reference_surface():
         DispatchConfig(uneven_shard=True)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_planner_random_slices_fuzz(seed):
+    """Seeded fuzz of the whole planner: random area-disjoint slices of all four types (random grid cells), random cp,
+    chunk size and stage count, through the full simulated CP forward/backward against the global oracle."""
+    import numpy as np
+
+    rng = np.random.default_rng(4321 + seed)
+    cp = int(rng.choice([2, 3, 4, 8]))
+    chunk = int(rng.choice([8, 16, 32]))
+    T = chunk * cp * int(rng.integers(1, 5))
+    degree = int(rng.integers(1, 4))
+
+    def cuts(n):
+        c = sorted(set([0, n] + [int(x) for x in rng.integers(1, max(n, 2), size=int(rng.integers(1, 6)))]))
+        return [(a, b) for a, b in zip(c[:-1], c[1:]) if b > a]
+
+    sl = []
+    for (q0, q1) in cuts(T):
+        for (k0, k1) in cuts(T):
+            if rng.random() < 0.6:
+                sl.append((q0, q1, k0, k1, int(rng.integers(0, 4))))
+    _simulate(sl, T, cp, chunk, degree, seed=seed)
+
+
 # magi_attention/api/__init__.py __all__ of the reference (names only, snapshot taken by listing the module's __all__)
 REFERENCE_API_ALL = ['magi_attn_varlen_key', 'magi_attn_varlen_dispatch', 'magi_attn_flex_key', 'magi_attn_flex_dispatch', 'dispatch', 'undispatch', 'roll', 'roll_simple', 'calc_attn', 'clear_cache', 'get_most_recent_key', 'get_position_ids', 'make_varlen_key_for_new_mask_after_dispatch', 'make_flex_key_for_new_mask_after_dispatch', 'flex_flash_attn_func', 'compute_pad_size', 'squash_batch_dim', 'infer_varlen_mask_from_batch', 'infer_attn_mask_from_sliding_window', 'infer_attn_mask_from_cu_seqlens', 'AttnForwardMeta', 'AttnMaskType', 'AttnOverlapMode', 'AttnRanges', 'DistAttnRuntimeKey', 'GeneralAttnMaskType', 'DistAttnConfig', 'DispatchConfig', 'OverlapConfig', 'GrpCollConfig', 'DispatchAlg', 'MinHeapDispatchAlg', 'ToppHeapDispatchAlg', 'SequentialDispatchAlg', 'SortedSequentialSelectAlg', 'LBDispatchAlg', 'DPDispatchAlg', 'BSDispatchAlg', 'OverlapAlg', 'UniformOverlapAlg', 'GreedyOverlapAlg', 'DistAttnRuntimeDictManager', 'dist_attn_runtime_dict_mgr']
 
