@@ -1,0 +1,229 @@
+// probe2cta.cu — on-device check of the cta_group::2 (CTA-pair) UMMA forms the next kernels need.
+//
+// One cluster of two CTAs computes D[256 x 128] = A[256 x 128] * B[128 x 128]^T (bf16, fp32 accumulate):
+//   * each CTA TMA-loads ITS 128 rows of A and ITS 64 rows (= half of N) of B into its own shared memory,
+//   * the leader CTA issues 8 K-steps of tcgen05.mma.cta_group::2 (M = 256, N = 128): the pair's tensor cores read
+//     A from their own SM and both halves of B across the pair, accumulators land in each CTA's own TMEM,
+//   * tcgen05.commit.cta_group::2 multicasts the completion to an mbarrier in both CTAs,
+//   * each CTA reads its 128 x 128 accumulator back and stores rows [128*rank, 128*rank+128).
+// Case 2 repeats the product with A taken from TMEM (the P / dS^T operand form of the attention kernels).
+// NOT YET RUN ON HARDWARE (written after the round-1 GPU budget was spent): run it before building on it.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o tools/probe/probe2cta tools/probe/probe2cta.cu -lcuda
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include "../../magiattention_b200/csrc/sm100.cuh"
+
+using namespace sm100;
+
+#define CK(x)                                                                                   \
+  do {                                                                                          \
+    cudaError_t e_ = (x);                                                                       \
+    if (e_ != cudaSuccess) {                                                                    \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__);           \
+      exit(2);                                                                                  \
+    }                                                                                           \
+  } while (0)
+
+typedef CUresult (*EncodeTiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// ---- cta_group::2 forms (kept local to the probe until they are validated) ------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t slot_smem, uint32_t ncols) {  // one warp of EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma2_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// completion of all prior cta_group::2 MMAs -> mbarrier at the same shared offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit2(uint32_t bar_smem, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar_smem), "h"(mask)
+               : "memory");
+}
+
+struct Args2 {
+  int a_src;  // 0 = A from shared memory (SS), 2 = A from TMEM (TS)
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+probe2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __nv_bfloat16* __restrict__ Ag, float* __restrict__ D, Args2 args) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;          // 128 rows x 128 K: 2 boxes [128 rows][64 cols] of 16 KB
+  uint8_t* sB = smem + 32768;  // 64 rows (this CTA's half of N) x 128 K: 2 boxes [64 rows][64 cols] of 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 49152);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 49152 + 64);
+  const uint32_t bar_tma = smem_u32(&bars[0]);
+  const uint32_t bar_mma = smem_u32(&bars[1]);
+  const int tid = threadIdx.x, wid = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+
+  if (tid == 0) {
+    mbar_init(bar_tma, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (wid == 0) {
+    tmem_alloc2(smem_u32(tmem_slot), 256);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_tma, 16384 + (args.a_src == 0 ? 32768 : 0));
+    if (args.a_src == 0) {
+      tma_load_2d(smem_u32(sA), &tmA, bar_tma, 0, int(rank) * 128);
+      tma_load_2d(smem_u32(sA + 16384), &tmA, bar_tma, 64, int(rank) * 128);
+    }
+    tma_load_2d(smem_u32(sB), &tmB, bar_tma, 0, int(rank) * 64);
+    tma_load_2d(smem_u32(sB + 8192), &tmB, bar_tma, 64, int(rank) * 64);
+  }
+  if (args.a_src == 2) {
+    // this CTA's A rows (row = 128*rank + tid) -> its own TMEM columns [128,192) as packed bf16 pairs
+    const uint32_t* arow = reinterpret_cast<const uint32_t*>(Ag + (size_t(rank) * 128 + tid) * 128);
+    uint32_t r[32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = arow[c * 32 + i];
+      tmem_st32(tmem + (uint32_t(wid * 32) << 16) + 128 + c * 32, r);
+    }
+    tc_wait_st();
+  }
+  mbar_wait(bar_tma, 0);  // own operands have landed
+  tc_fence_before();
+  cluster_sync_all();     // ... and the peer's too (a pipelined kernel signals the leader's mbarrier instead)
+  tc_fence_after();
+
+  if (rank == 0 && wid == 0) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(true, false, false, 256, 128);
+#pragma unroll 1
+      for (uint32_t k = 0; k < 8; ++k) {
+        const uint64_t bd = smem_desc(DESC_KMAJOR, smem_u32(sB) + (k >> 2) * 8192 + (k & 3) * 32);
+        if (args.a_src == 0) {
+          const uint64_t ad = smem_desc(DESC_KMAJOR, smem_u32(sA) + (k >> 2) * 16384 + (k & 3) * 32);
+          mma2_ss(tmem, ad, bd, idesc, k > 0);
+        } else {
+          mma2_ts(tmem, tmem + 128 + k * 8, bd, idesc, k > 0);
+        }
+      }
+      tc_commit2(bar_mma, 0x3);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32];
+    tmem_ld32(tmem + (uint32_t(wid * 32) << 16) + c * 32, r);
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) D[(size_t(rank) * 128 + tid) * 128 + c * 32 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  cluster_sync_all();  // nobody frees TMEM / exits while the pair's MMA may still touch the peer
+  if (wid == 0) tmem_dealloc2(tmem, 256);
+}
+
+static float bf2f(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+int main() {
+  CK(cudaSetDevice(0));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  EncodeTiled_t encode = (EncodeTiled_t)fn;
+  const int M = 256, N = 128, K = 128;
+  std::vector<__nv_bfloat16> hA(M * K), hB(N * K);
+  srand(4321);
+  for (auto& x : hA) x = __float2bfloat16((rand() % 2001 - 1000) / 1000.f);
+  for (auto& x : hB) x = __float2bfloat16((rand() % 2001 - 1000) / 1000.f);
+  __nv_bfloat16 *dA, *dB;
+  float* dD;
+  CK(cudaMalloc(&dA, M * K * 2));
+  CK(cudaMalloc(&dB, N * K * 2));
+  CK(cudaMalloc(&dD, M * N * 4));
+  CK(cudaMemcpy(dA, hA.data(), M * K * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), N * K * 2, cudaMemcpyHostToDevice));
+  auto make_map = [&](void* ptr, int rows, int box_rows) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {cuuint64_t(K), cuuint64_t(rows)};
+    cuuint64_t strides[1] = {cuuint64_t(K) * 2};
+    cuuint32_t box[2] = {64, cuuint32_t(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      printf("encode failed %d\n", (int)r);
+      exit(2);
+    }
+    return m;
+  };
+  CUtensorMap tmA = make_map(dA, M, 128), tmB = make_map(dB, N, 64);
+  CK(cudaFuncSetAttribute(probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
+  int n_fail = 0;
+  const char* names[2] = {"2-CTA SS  A=K-major B=K-major  M=256 N=128", "2-CTA TS  A=TMEM    B=K-major  M=256 N=128"};
+  for (int cs = 0; cs < 2; ++cs) {
+    Args2 a{cs == 0 ? 0 : 2};
+    CK(cudaMemset(dD, 0xff, M * N * 4));
+    probe2_kernel<<<2, 128, 56 * 1024>>>(tmA, tmB, dA, dD, a);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("[FAIL] %-48s : launch error %s\n", names[cs], cudaGetErrorString(e));
+      return 3;
+    }
+    std::vector<float> hD(M * N);
+    CK(cudaMemcpy(hD.data(), dD, M * N * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0, maxref = 0;
+    for (int m = 0; m < M; ++m)
+      for (int n = 0; n < N; ++n) {
+        float acc = 0;
+        for (int k = 0; k < K; ++k) acc += bf2f(hA[m * K + k]) * bf2f(hB[n * K + k]);
+        double err = fabs(double(acc) - double(hD[m * N + n]));
+        if (!(err <= 1e30)) err = 1e30;
+        maxerr = fmax(maxerr, err);
+        maxref = fmax(maxref, fabs(acc));
+      }
+    bool ok = maxerr < 1e-2;
+    n_fail += !ok;
+    printf("[%s] %-48s : max|err| = %.3e (max|ref| = %.2f)\n", ok ? "PASS" : "FAIL", names[cs], maxerr, maxref);
+  }
+  printf("probe2cta done: %d failing cases\n", n_fail);
+  return n_fail ? 1 : 0;
+}
