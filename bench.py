@@ -193,6 +193,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
+        # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ..." under NCCL_DEBUG=VERSION/INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()  # fail loudly if the CUDA library is missing
 
