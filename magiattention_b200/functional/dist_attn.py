@@ -25,6 +25,7 @@ import os
 import torch
 import torch.distributed as dist
 
+from .. import _lib
 from ..comm.group_collective import group_cast, group_reduce
 from ..comm.work import WorkWithPostProcessFn
 from ..common.forward_meta import AttnForwardMeta
@@ -172,7 +173,6 @@ class DistAttnFunc(torch.autograd.Function):
                 dv_p = torch.empty(rv.shape, dtype=wire, device=rv.device)
                 a = arg.to_ffa_args(q.device)
                 # fresh (non-accumulating) partial dk/dv in the wire dtype; dq accumulates
-                from .. import _lib
                 _lib.ffa_bwd(dout, q, rk, rv, out, lse, dq, dk_p, dv_p, a["q_ranges"], a["k_ranges"], a["attn_type_map"],
                              scale, softcap, accumulate_dkv=False, sm_margin=runtime.sm_margin)
             reduces.append(runtime.reduce_partial_dkv(st, dk_p, dv_p, dk, dv))
