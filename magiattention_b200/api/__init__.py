@@ -1,6 +1,7 @@
 """User-facing API (mirror of magi_attention/api/__init__.py)."""
 from ..functional.flex_flash_attn import flex_flash_attn_func  # noqa: F401
 from .functools import (  # noqa: F401
+    apply_padding,
     compute_pad_size,
     infer_attn_mask_from_cu_seqlens,
     infer_attn_mask_from_sliding_window,

@@ -10,7 +10,7 @@ from ..common.ranges import AttnRanges
 from ..meta.planner import _restrict
 
 __all__ = ["compute_pad_size", "squash_batch_dim", "infer_varlen_mask_from_batch", "infer_attn_mask_from_sliding_window",
-           "infer_attn_mask_from_cu_seqlens", "pad_at_dim", "unpad_at_dim"]
+           "infer_attn_mask_from_cu_seqlens", "pad_at_dim", "unpad_at_dim", "apply_padding"]
 
 
 def compute_pad_size(total_seqlen_q: int, cp_size: int, chunk_size: int) -> int:
@@ -25,10 +25,27 @@ def squash_batch_dim(x: torch.Tensor) -> torch.Tensor:
     return x.reshape(x.shape[0] * x.shape[1], *x.shape[2:])
 
 
-def infer_varlen_mask_from_batch(batch_size: int, seq_len: int) -> tuple[torch.Tensor, torch.Tensor]:
-    """cu_seqlens_q/k of a [b, s] batch flattened to one packed sequence (reference :68-91)."""
-    cu = torch.arange(0, (batch_size + 1) * seq_len, seq_len, dtype=torch.int32)
-    return cu, cu.clone()
+def infer_varlen_mask_from_batch(batch_size: int, seq_len: int, device: str | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """cu_seqlens_q/k (int32 ``[batch_size + 1]``) of a [b, s] batch flattened to one packed sequence (reference :68-91;
+    ``device`` defaults to "cuda" like the reference when a GPU is present)."""
+    if device is None:
+        device = "cuda" if torch.cuda.is_available() else "cpu"
+    cu = torch.arange(0, batch_size + 1, dtype=torch.int32, device=device) * seq_len
+    return cu, cu
+
+
+def apply_padding(q_ranges: AttnRanges, k_ranges: AttnRanges, attn_mask_type: list, total_seqlen: int,
+                  pad_size: int) -> tuple[AttnRanges, AttnRanges, list]:
+    """Append the padding rows ``[total_seqlen, total_seqlen + pad_size)`` as a q range with an empty k range and a FULL type
+    — a slice that attends to nothing, so padded rows come out as 0 / -inf (reference :142-177).  The key builders here do
+    not need it (uncovered rows already behave that way); it exists for callers that build slice lists themselves."""
+    qr = AttnRanges.from_ranges(q_ranges.to_naive_ranges())
+    kr = AttnRanges.from_ranges(k_ranges.to_naive_ranges())
+    ty = list(attn_mask_type)
+    qr.append(AttnRange(total_seqlen, total_seqlen + pad_size))
+    kr.append(AttnRange(0, 0))
+    ty.append(AttnMaskType.FULL)
+    return qr, kr, ty
 
 
 def pad_at_dim(x: torch.Tensor, dim: int, pad_size: int, value: float = 0.0, side: str = "right") -> torch.Tensor:

@@ -153,3 +153,59 @@ def test_correct_attn_helpers_match_oracle_merge():
         so, sl = orc.merge_out_lse(ro, rl, torch.zeros_like(ro), ls)
         torch.testing.assert_close(correct_attn_lse_with_sink(rl, sink, layout), sl)
         torch.testing.assert_close(correct_attn_out_with_sink(ro, rl, sink, layout), so)
+
+
+def test_mask_helpers_match_reference_functools():
+    """infer_attn_mask_from_sliding_window / infer_attn_mask_from_cu_seqlens produce the same DENSE mask as the reference's
+    helpers on a sweep of inputs (fixture: tests/golden/functools_masks.json from gen_functools_golden.py).  The slice lists may
+    legitimately be cut differently; what is pinned is the set of (q, k) pairs, and that our slices are area-disjoint."""
+    import json
+
+    from magiattention_b200.api import infer_attn_mask_from_cu_seqlens, infer_attn_mask_from_sliding_window
+    from magiattention_b200.common import AttnRange
+
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "functools_masks.json")))
+    assert len(g["sliding_window"]) >= 90 and len(g["cu_seqlens"]) >= 40
+
+    def dense(qr, kr, ty, tq, tk):
+        return orc.mask_from_slices(qr, kr, ty, tq, tk)
+
+    def check(ours, ref, tq, tk, what):
+        qr, kr, ty = ours
+        m = dense(qr, kr, ty, tq, tk)
+        assert torch.equal(m, dense(ref["q_ranges"], ref["k_ranges"], ref["types"], tq, tk)), what
+        assert orc.mask_area(qr, kr, ty) == int(m.sum()), f"{what}: slices overlap"
+
+    for c in g["sliding_window"]:
+        qr, kr, ty = infer_attn_mask_from_sliding_window(AttnRange(*c["q_range"]), AttnRange(*c["k_range"]), tuple(c["window"]))
+        check((qr.to_naive_ranges(), kr.to_naive_ranges(), [t.to_int_type() for t in ty]), c, c["q_range"][1], c["k_range"][1],
+              f"sliding window {c['q_range']} x {c['k_range']} w={c['window']}")
+    for c in g["cu_seqlens"]:
+        qr, kr, ty, tq, tk = infer_attn_mask_from_cu_seqlens(torch.tensor(c["cu_q"], dtype=torch.int32),
+                                                             torch.tensor(c["cu_k"], dtype=torch.int32), causal=c["causal"],
+                                                             window_size=tuple(c["window"]))
+        assert (int(tq), int(tk)) == (c["total_q"], c["total_k"])
+        check((qr.to_naive_ranges(), kr.to_naive_ranges(), [t.to_int_type() for t in ty]), c, c["total_q"], c["total_k"],
+              f"cu_seqlens {c['cu_q']} / {c['cu_k']} causal={c['causal']} w={c['window']}")
+
+
+def test_small_api_helpers_known_answers():
+    """compute_pad_size / squash_batch_dim / infer_varlen_mask_from_batch / pad_at_dim / unpad_at_dim / apply_padding: values
+    obtained by running the reference's functions (api/functools.py:27-177) on the same arguments."""
+    from magiattention_b200.api import (apply_padding, compute_pad_size, infer_varlen_mask_from_batch, pad_at_dim,
+                                        squash_batch_dim, unpad_at_dim)
+    from magiattention_b200.common import AttnRanges
+
+    for args, want in (((1000, 4, 128), 24), ((4096, 8, 512), 0), ((1, 2, 16), 31), ((2048, 2, 1024), 0), ((777, 3, 64), 183)):
+        assert compute_pad_size(*args) == want
+    x = torch.arange(24).reshape(2, 3, 4)
+    assert torch.equal(squash_batch_dim(x), x.reshape(6, 4))
+    cq, ck = infer_varlen_mask_from_batch(3, 5, device="cpu")
+    assert cq.tolist() == ck.tolist() == [0, 5, 10, 15] and cq.dtype == torch.int32
+    y = torch.arange(12.0).reshape(3, 4)
+    assert pad_at_dim(y, 0, 2).shape == (5, 4) and pad_at_dim(y, 0, 2)[3:].eq(0).all()
+    assert pad_at_dim(y, 1, 3, value=-1.0)[:, 4:].eq(-1).all() and torch.equal(pad_at_dim(y, 0, 1, side="left")[1:], y)
+    assert torch.equal(unpad_at_dim(pad_at_dim(y, 0, 2), 0, 2), y)
+    qr, kr, ty = apply_padding(AttnRanges.from_ranges([[0, 10]]), AttnRanges.from_ranges([[0, 10]]), [1], 10, 6)
+    assert qr.to_naive_ranges() == [(0, 10), (10, 16)] or qr.to_naive_ranges() == [[0, 10], [10, 16]]
+    assert list(map(tuple, kr.to_naive_ranges())) == [(0, 10), (0, 0)] and len(ty) == 2
