@@ -280,6 +280,45 @@ def test_planner_random_slices_fuzz(seed):
     _simulate(sl, T, cp, chunk, degree, seed=seed)
 
 
+def test_dispatch_load_balance_matches_reference_planner():
+    """Our min-heap dispatch against the partitions the reference's own planner (make_dispatch_meta_from_qk_ranges, MinHeap)
+    emits for the same masks (fixture: tests/golden/dispatch_partitions.json, gen_dispatch_golden.py): equal chunk counts and
+    a heaviest-rank mask area no worse than the reference's.  On the pure causal mask both give the zig-zag pairing."""
+    import json
+    import os
+
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "dispatch_partitions.json")))
+    assert len(cases) >= 18
+    for c in cases:
+        sl = [(q[0], q[1], k[0], k[1], t) for q, k, t in zip(c["q_ranges"], c["k_ranges"], c["types"])]
+        T, cs, cp = c["total_seqlen"], c["chunk_size"], c["cp_size"]
+        dm = make_dispatch_meta(sl, T, cs, cp)
+
+        def rank_areas(parts):
+            return [sum(slice_area(s, ch * cs, (ch + 1) * cs) for ch in p for s in sl if s[1] > s[0] and s[3] > s[2]) for p in parts]
+
+        ours, ref = rank_areas(dm.partitions), rank_areas(c["partitions"])
+        assert sum(ours) == sum(ref)
+        assert sorted(len(p) for p in dm.partitions) == sorted(len(p) for p in c["partitions"])
+        assert max(ours) <= max(ref) * 1.0001 + 1, (c["name"], cp, max(ours), max(ref))
+        if c["name"] == "causal_64chunks":
+            assert sorted(map(tuple, dm.partitions)) == sorted(map(tuple, c["partitions"]))
+
+
+def test_c4_plan_matches_reference_planner_known_answers():
+    """BASELINE config C4 (S = 262144 causal, cp = 8, chunk 2048): the numbers the reference's own planner produces for it
+    (obtained by running DistAttnSolver on CPU): zig-zag partitions, zero-redundant remote KV volume of
+    229376 (rank 0) ... 215040 (rank 7) rows, perfectly balanced mask area."""
+    S, cp, cs = 262144, 8, 2048
+    sl = [(0, S, 0, S, 1)]
+    dm = make_dispatch_meta(sl, S, cs, cp)
+    assert dm.partitions[0][:6] == [0, 15, 16, 31, 32, 47] and dm.partitions[7][:6] == [7, 8, 23, 24, 39, 40]
+    comm, calc = make_attn_meta(sl, dm, 2)
+    assert [sum(c.num_remote_kv_tokens_per_stage) for c in comm] == [229376 - 2048 * r for r in range(cp)]
+    areas = [c.local_attn_arg.total_area + sum(a.total_area for a in c.remote_attn_args_list) for c in calc]
+    assert len(set(areas)) == 1 and sum(areas) == S * (S + 1) // 2
+
+
 # magi_attention/api/__init__.py __all__ of the reference (names only, snapshot taken by listing the module's __all__)
 REFERENCE_API_ALL = ['magi_attn_varlen_key', 'magi_attn_varlen_dispatch', 'magi_attn_flex_key', 'magi_attn_flex_dispatch', 'dispatch', 'undispatch', 'roll', 'roll_simple', 'calc_attn', 'clear_cache', 'get_most_recent_key', 'get_position_ids', 'make_varlen_key_for_new_mask_after_dispatch', 'make_flex_key_for_new_mask_after_dispatch', 'flex_flash_attn_func', 'compute_pad_size', 'squash_batch_dim', 'infer_varlen_mask_from_batch', 'infer_attn_mask_from_sliding_window', 'infer_attn_mask_from_cu_seqlens', 'AttnForwardMeta', 'AttnMaskType', 'AttnOverlapMode', 'AttnRanges', 'DistAttnRuntimeKey', 'GeneralAttnMaskType', 'DistAttnConfig', 'DispatchConfig', 'OverlapConfig', 'GrpCollConfig', 'DispatchAlg', 'MinHeapDispatchAlg', 'ToppHeapDispatchAlg', 'SequentialDispatchAlg', 'SortedSequentialSelectAlg', 'LBDispatchAlg', 'DPDispatchAlg', 'BSDispatchAlg', 'OverlapAlg', 'UniformOverlapAlg', 'GreedyOverlapAlg', 'DistAttnRuntimeDictManager', 'dist_attn_runtime_dict_mgr']
 
