@@ -92,7 +92,8 @@ class DistAttnRuntimeMgr:
         self.all_calc_metas = calc_metas  # kept for FLOP / balance accounting
         self.all_comm_metas = comm_metas
         self.dist_attn_runtime = DistAttnRuntime(self.comm_meta, self.calc_meta, cp_group,
-                                                 high_precision_reduce=key.config.high_precision_reduce)
+                                                 high_precision_reduce=key.config.high_precision_reduce,
+                                                 all_comm_metas=comm_metas)
         self._position_ids: torch.Tensor | None = None
 
     # ---- dispatch / undispatch (reference :162-245) ------------------------------------------------

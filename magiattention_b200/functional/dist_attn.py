@@ -39,7 +39,7 @@ class DistAttnRuntime:
     """Holds the per-key metadata and implements the stage primitives (reference :141-239)."""
 
     def __init__(self, comm_meta: CommMeta, calc_meta: CalcMeta, cp_group: dist.ProcessGroup | None,
-                 sm_margin: int = 0, high_precision_reduce: bool = False):
+                 sm_margin: int = 0, high_precision_reduce: bool = False, all_comm_metas: list[CommMeta] | None = None):
         self.comm_meta = comm_meta
         self.calc_meta = calc_meta
         self.cp_group = cp_group
@@ -49,10 +49,15 @@ class DistAttnRuntime:
         self.cp_size = 1 if cp_group is None else dist.get_world_size(cp_group)
         # communication volume bookkeeping (rows of K == rows of V) for exposed-comm accounting
         self.remote_rows_per_stage = list(comm_meta.num_remote_kv_tokens_per_stage)
+        # opt-in experimental engine: KV pulled over NVLink peer memory instead of NCCL P2P (comm/peer_exchange.py)
+        self.all_comm_metas = all_comm_metas
+        self._peer_fetchers: dict = {}
 
     # ---- communication ---------------------------------------------------------------------------
     def fetch_remote_kv(self, k: torch.Tensor, v: torch.Tensor) -> list[WorkWithPostProcessFn | None]:
         """One async group_cast per stage, all issued now (reference: _fetch_remote_kv :1463-1567)."""
+        if os.environ.get("MAGI_B200_KV_EXCHANGE", "nccl") == "peer" and self.cp_size > 1 and self.all_comm_metas is not None:
+            return self._peer_fetcher(k).fetch(k, v)
         works: list[WorkWithPostProcessFn | None] = []
         for st in range(self.overlap_degree):
             if self.calc_meta.remote_attn_args_list[st].can_skip and self.remote_rows_per_stage[st] == 0 \
@@ -62,6 +67,18 @@ class DistAttnRuntime:
             arg = self.comm_meta.kv_group_collective_args_list[st]
             works.append(group_cast((k, v), None, group=self.cp_group, async_op=True, **arg.to_group_cast_args()))
         return works
+
+    def _peer_fetcher(self, k: torch.Tensor):
+        from ..comm.peer_exchange import PeerKVFetcher
+
+        key = (k.dtype, k.shape[1], k.shape[2], k.device)
+        f = self._peer_fetchers.get(key)
+        if f is None:  # collective: every rank builds it on its first fetch with this geometry
+            per_stage = [[cm.kv_group_collective_args_list[st] for cm in self.all_comm_metas] for st in range(self.overlap_degree)]
+            f = PeerKVFetcher(self.cp_group, dist.get_rank(self.cp_group), per_stage, k.shape[0], k.shape[1], k.shape[2], k.dtype,
+                              k.device)
+            self._peer_fetchers[key] = f
+        return f
 
     def reduce_partial_dkv(self, st: int, dk_part: torch.Tensor, dv_part: torch.Tensor, dk: torch.Tensor,
                            dv: torch.Tensor) -> WorkWithPostProcessFn:

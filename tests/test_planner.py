@@ -280,6 +280,33 @@ def test_planner_random_slices_fuzz(seed):
     _simulate(sl, T, cp, chunk, degree, seed=seed)
 
 
+@pytest.mark.parametrize("cp,degree", [(2, 1), (4, 2), (8, 3)])
+def test_pull_plan_equals_group_cast(cp, degree):
+    """comm/peer_exchange.make_pull_plan (the host side of the opt-in peer-memory exchange): pulling the listed row spans
+    out of the owners' shards reproduces the receive buffer of the naive group_cast for every rank and stage."""
+    from magiattention_b200.comm.peer_exchange import make_pull_plan
+
+    for cfg in mask_configs(4):
+        sl = _slices(cfg)
+        chunk = 16
+        T = cfg["seqlen"] + (-cfg["seqlen"]) % (chunk * cp)
+        dm = make_dispatch_meta(sl, T, chunk, cp)
+        comm, _ = make_attn_meta(sl, dm, degree)
+        kg = torch.arange(T * 2, dtype=torch.float64).reshape(T, 2)
+        kl = [kg[dm.position_ids(r)] for r in range(cp)]
+        for st in range(degree):
+            args = [comm[r].kv_group_collective_args_list[st] for r in range(cp)]
+            kw = dict(input_split_sizes=[a.input_split_size_list for a in args], dst_indices=[a.dst_indices_list for a in args],
+                      src_index=[a.src_index_list for a in args], output_split_sizes=[a.output_split_size_list for a in args])
+            want = orc.group_cast_ref(kl, **kw)
+            for r in range(cp):
+                out = torch.full_like(want[r], -1)
+                for (s, s0, d0, n) in make_pull_plan(args, r):
+                    assert s != r
+                    out[d0:d0 + n] = kl[s][s0:s0 + n]
+                assert torch.equal(out, want[r])
+
+
 def test_dispatch_load_balance_matches_reference_planner():
     """Our min-heap dispatch against the partitions the reference's own planner (make_dispatch_meta_from_qk_ranges, MinHeap)
     emits for the same masks (fixture: tests/golden/dispatch_partitions.json, gen_dispatch_golden.py): equal chunk counts and
