@@ -22,7 +22,7 @@ import torch.distributed as dist
 
 from .work import GeneralWork, WorkWithPostProcessFn
 
-__all__ = ["make_pull_plan", "PeerKVFetcher"]
+__all__ = ["make_pull_plan", "make_reduce_pull_plan", "PeerKVFetcher"]
 
 
 def make_pull_plan(cast_args_all_ranks: list, rank: int) -> list[tuple[int, int, int, int]]:
@@ -54,6 +54,35 @@ def make_pull_plan(cast_args_all_ranks: list, rank: int) -> list[tuple[int, int,
             else:
                 plan.append((s, s0, dst, sz))
         dst += sz
+    return plan
+
+
+def make_reduce_pull_plan(cast_args_all_ranks: list, owner: int) -> list[tuple[int, int, int, int]]:
+    """The return path (partial dK/dV of one stage) as pulls by the OWNER: ``(consumer_rank, src_row0 in the consumer's stage
+    buffer, dst_row0 in the owner's local rows, nrows)``; the owner adds every listed span into its dk/dv (the fused row-span
+    add can read the peer rows directly = reduce-on-receive).  Transpose of :func:`make_pull_plan`: entries with the same
+    destination span are adjacent, which is what ``b200_range_reduce_sum`` needs to fold them in one race-free pass."""
+    mine = cast_args_all_ranks[owner]
+    # per consumer: offsets (in ITS stage buffer) of the output splits that came from `owner`, in order
+    offsets: dict[int, list[tuple[int, int]]] = {}
+    for d, arg in enumerate(cast_args_all_ranks):
+        off, lst = 0, []
+        for sz, s in zip(arg.output_split_size_list, arg.src_index_list):
+            if sz > 0 and s == owner:
+                lst.append((off, sz))
+            off += sz
+        offsets[d] = lst
+    cursor = {d: 0 for d in offsets}
+    plan: list[tuple[int, int, int, int]] = []
+    loc = 0
+    for sz, dsts in zip(mine.input_split_size_list, mine.dst_indices_list):
+        if sz > 0:
+            for d in dsts:
+                s0, ssz = offsets[d][cursor[d]]
+                cursor[d] += 1
+                assert ssz == sz, "transfer tables of sender and receiver disagree"
+                plan.append((d, s0, loc, sz))
+        loc += sz
     return plan
 
 

@@ -305,6 +305,21 @@ def test_pull_plan_equals_group_cast(cp, degree):
                     assert s != r
                     out[d0:d0 + n] = kl[s][s0:s0 + n]
                 assert torch.equal(out, want[r])
+            # return path: every owner pulls the partial rows of its consumers and adds them == naive group_reduce
+            from magiattention_b200.comm.peer_exchange import make_reduce_pull_plan
+
+            parts = [torch.randn(w.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(r + 7 * st))
+                     for r, w in enumerate(want)]
+            acc0 = [torch.zeros_like(x) for x in kl]
+            rkw = [a.to_group_reduce_args() for a in args]
+            ref = orc.group_reduce_ref(parts, [a.clone() for a in acc0], input_split_sizes=[a["input_split_sizes"] for a in rkw],
+                                       dst_index=[a["dst_index"] for a in rkw], src_indices=[a["src_indices"] for a in rkw],
+                                       output_split_sizes=[a["output_split_sizes"] for a in rkw])
+            for o in range(cp):
+                acc = acc0[o].clone()
+                for (d, s0, l0, n) in make_reduce_pull_plan(args, o):
+                    acc[l0:l0 + n] += parts[d][s0:s0 + n]
+                torch.testing.assert_close(acc, ref[o], atol=1e-12, rtol=1e-12)
 
 
 def test_dispatch_load_balance_matches_reference_planner():
