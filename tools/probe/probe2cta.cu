@@ -7,7 +7,8 @@
 //   * tcgen05.commit.cta_group::2 multicasts the completion to an mbarrier in both CTAs,
 //   * each CTA reads its 128 x 128 accumulator back and stores rows [128*rank, 128*rank+128).
 // Case 2 repeats the product with A taken from TMEM (the P / dS^T operand form of the attention kernels).
-// NOT YET RUN ON HARDWARE (written after the round-1 GPU budget was spent): run it before building on it.
+// Validated on a B200 (profiles/r01_probe2cta.txt): both cases pass — the B operand really is split across the pair by N halves
+// at the same shared-memory offset in both CTAs, and the TMEM-A form works with each CTA's own TMEM rows.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o tools/probe/probe2cta tools/probe/probe2cta.cu -lcuda
 #include <cuda.h>
 #include <cstdlib>
