@@ -49,10 +49,10 @@ __host__ __device__ __forceinline__ bool row_hull(const Slice& s, int c_lo, int 
   return r_max > r_min;
 }
 
-// Does the slice contribute anything to forward CTA tile [R0, R0+256)?
-__host__ __device__ __forceinline__ bool fwd_tile_hit(const Slice& s, int R0) {
+// Does the slice contribute anything to the forward tile of `rows` q rows starting at R0 (256 per CTA, 512 per CTA pair)?
+__host__ __device__ __forceinline__ bool fwd_tile_hit(const Slice& s, int R0, int rows = kFwdTileQ) {
   int r_lo = s.q0 > R0 ? s.q0 : R0;
-  int r_hi = s.q1 < R0 + kFwdTileQ ? s.q1 : R0 + kFwdTileQ;
+  int r_hi = s.q1 < R0 + rows ? s.q1 : R0 + rows;
   int a, b;
   return col_hull(s, r_lo, r_hi, a, b);
 }

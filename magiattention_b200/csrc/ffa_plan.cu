@@ -30,7 +30,7 @@ plan_kernel(SliceMeta meta, int n_tiles, int tile_rows, int capacity, int* __res
       for (int s = 0; s < meta.num_slices; ++s) {
         int2 q = __ldg(meta.q_ranges + s), k = __ldg(meta.k_ranges + s);
         Slice sl{q.x, q.y, k.x, k.y, meta.types ? __ldg(meta.types + s) : 0};
-        cnt += (kFwd ? fwd_tile_hit(sl, T0) : bwd_tile_hit(sl, T0)) ? 1 : 0;
+        cnt += (kFwd ? fwd_tile_hit(sl, T0, tile_rows) : bwd_tile_hit(sl, T0)) ? 1 : 0;
       }
     }
     // block exclusive scan of cnt
@@ -75,9 +75,15 @@ plan_kernel(SliceMeta meta, int n_tiles, int tile_rows, int capacity, int* __res
     for (int s = 0; s < meta.num_slices; ++s) {
       int2 q = __ldg(meta.q_ranges + s), k = __ldg(meta.k_ranges + s);
       Slice sl{q.x, q.y, k.x, k.y, meta.types ? __ldg(meta.types + s) : 0};
-      if (kFwd ? fwd_tile_hit(sl, T0) : bwd_tile_hit(sl, T0)) ids[o++] = s;
+      if (kFwd ? fwd_tile_hit(sl, T0, tile_rows) : bwd_tile_hit(sl, T0)) ids[o++] = s;
     }
   }
+}
+
+// forward plan over tiles of `tile_rows` q rows (512 for the CTA-pair forward)
+cudaError_t launch_plan_fwd_rows(const SliceMeta& meta, int n_tiles, int tile_rows, int capacity, int* plan, cudaStream_t stream) {
+  plan_kernel<true><<<1, 1024, 0, stream>>>(meta, n_tiles, tile_rows, capacity, plan);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_plan(bool fwd, const SliceMeta& meta, int n_tiles, int capacity, int* plan, cudaStream_t stream) {
