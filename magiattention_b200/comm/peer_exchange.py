@@ -13,7 +13,7 @@ HARDWARE; the default engine is ``group_cast`` over NCCL (comm/group_collective.
     error ends in an exception instead of a hung box.
 
 The pull tables are derived on the host from the planner's transfer tables of ALL ranks (the planner is deterministic, every
-rank holds every table): ``make_pull_plan`` is pure Python and is unit-tested on CPU against the oracle's group_cast.
+rank holds every table): ``make_pull_plan`` is pure Python and is unit-tested on CPU against the naive world-level group_cast.
 """
 from __future__ import annotations
 
