@@ -7,7 +7,9 @@
 //   * tcgen05.commit.cta_group::2 multicasts the completion to an mbarrier in both CTAs,
 //   * each CTA reads its 128 x 128 accumulator back and stores rows [128*rank, 128*rank+128).
 // Case 2 repeats the product with A taken from TMEM (the P / dS^T operand form of the attention kernels).
-// Validated on a B200 (profiles/r01_probe2cta.txt): both cases pass — the B operand really is split across the pair by N halves
+// Cases 3-4 (added after the hardware run, NOT YET RUN) repeat both with the barrier protocol of csrc/ffa_fwd2.cu: cta_group::2 TMA
+// loads completing on the leader's mbarrier (mapa) and 256 local + remote thread arrivals gating the leader's MMA.
+// Cases 1-2 validated on a B200 (profiles/r01_probe2cta.txt): both pass — the B operand really is split across the pair by N halves
 // at the same shared-memory offset in both CTAs, and the TMEM-A form works with each CTA's own TMEM rows.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o tools/probe/probe2cta tools/probe/probe2cta.cu -lcuda
 #include <cuda.h>
@@ -34,8 +36,20 @@ typedef CUresult (*EncodeTiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // the cta_group::2 wrappers under test live in csrc/sm100.cuh (cluster_ctarank, cluster_sync_all, tmem_alloc2, mma2_ss, mma2_ts, tc_commit2)
 
+// 2-D flavour of sm100::tma_load_3d_pair (the cta_group::2 load whose bytes complete on the leader's mbarrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 struct Args2 {
-  int a_src;  // 0 = A from shared memory (SS), 2 = A from TMEM (TS)
+  int a_src;     // 0 = A from shared memory (SS), 2 = A from TMEM (TS)
+  int protocol;  // 0 = every CTA waits its own TMA barrier, then a cluster barrier (validated);
+                 // 1 = the barrier protocol of csrc/ffa_fwd2.cu: all TMA loads of the pair complete on the LEADER's mbarrier
+                 //     (cp.async.bulk.tensor.cta_group::2 + mapa), and the leader's MMA is additionally gated by an mbarrier that
+                 //     collects one remote/local arrive from each of the 256 threads of the pair (the "P ready" barrier)
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
@@ -49,12 +63,14 @@ probe2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 49152 + 64);
   const uint32_t bar_tma = smem_u32(&bars[0]);
   const uint32_t bar_mma = smem_u32(&bars[1]);
+  const uint32_t bar_rdy = smem_u32(&bars[2]);
   const int tid = threadIdx.x, wid = tid >> 5;
   const uint32_t rank = cluster_ctarank();
 
   if (tid == 0) {
     mbar_init(bar_tma, 1);
     mbar_init(bar_mma, 1);
+    mbar_init(bar_rdy, 256);
     fence_barrier_init();
   }
   if (wid == 0) {
@@ -63,17 +79,30 @@ probe2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if (args.protocol == 1) cluster_sync_all();  // the leader's barriers exist before the peer targets them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
   if (tid == 0) {
-    mbar_arrive_expect_tx(bar_tma, 16384 + (args.a_src == 0 ? 32768 : 0));
-    if (args.a_src == 0) {
-      tma_load_2d(smem_u32(sA), &tmA, bar_tma, 0, int(rank) * 128);
-      tma_load_2d(smem_u32(sA + 16384), &tmA, bar_tma, 64, int(rank) * 128);
+    const uint32_t my_bytes = 16384 + (args.a_src == 0 ? 32768 : 0);
+    if (args.protocol == 0) {
+      mbar_arrive_expect_tx(bar_tma, my_bytes);
+      if (args.a_src == 0) {
+        tma_load_2d(smem_u32(sA), &tmA, bar_tma, 0, int(rank) * 128);
+        tma_load_2d(smem_u32(sA + 16384), &tmA, bar_tma, 64, int(rank) * 128);
+      }
+      tma_load_2d(smem_u32(sB), &tmB, bar_tma, 0, int(rank) * 64);
+      tma_load_2d(smem_u32(sB + 8192), &tmB, bar_tma, 64, int(rank) * 64);
+    } else {
+      const uint32_t leader_bar = mapa_shared(bar_tma, 0);
+      if (rank == 0) mbar_arrive_expect_tx(bar_tma, 2 * my_bytes);  // both CTAs' bytes land on the leader's barrier
+      if (args.a_src == 0) {
+        tma_load_2d_pair(smem_u32(sA), &tmA, leader_bar, 0, int(rank) * 128);
+        tma_load_2d_pair(smem_u32(sA + 16384), &tmA, leader_bar, 64, int(rank) * 128);
+      }
+      tma_load_2d_pair(smem_u32(sB), &tmB, leader_bar, 0, int(rank) * 64);
+      tma_load_2d_pair(smem_u32(sB + 8192), &tmB, leader_bar, 64, int(rank) * 64);
     }
-    tma_load_2d(smem_u32(sB), &tmB, bar_tma, 0, int(rank) * 64);
-    tma_load_2d(smem_u32(sB + 8192), &tmB, bar_tma, 64, int(rank) * 64);
   }
   if (args.a_src == 2) {
     // this CTA's A rows (row = 128*rank + tid) -> its own TMEM columns [128,192) as packed bf16 pairs
@@ -87,12 +116,23 @@ probe2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     tc_wait_st();
   }
-  mbar_wait(bar_tma, 0);  // own operands have landed
-  tc_fence_before();
-  cluster_sync_all();     // ... and the peer's too (a pipelined kernel signals the leader's mbarrier instead)
-  tc_fence_after();
+  if (args.protocol == 0) {
+    mbar_wait(bar_tma, 0);  // own operands have landed
+    tc_fence_before();
+    cluster_sync_all();     // ... and the peer's too
+    tc_fence_after();
+  } else {
+    // every thread of the pair (its TMEM A rows are written and fenced) arrives on the LEADER's ready barrier
+    tc_fence_before();
+    mbar_arrive_cluster(mapa_shared(bar_rdy, 0));
+  }
 
   if (rank == 0 && wid == 0) {
+    if (args.protocol == 1) {
+      mbar_wait(bar_tma, 0);  // the pair's operands (both CTAs) have landed
+      mbar_wait(bar_rdy, 0);  // 256 arrivals
+      tc_fence_after();
+    }
     if (elect_one()) {
       const uint32_t idesc = make_idesc(true, false, false, 256, 128);
 #pragma unroll 1
@@ -161,9 +201,10 @@ int main() {
   CUtensorMap tmA = make_map(dA, M, 128), tmB = make_map(dB, N, 64);
   CK(cudaFuncSetAttribute(probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
   int n_fail = 0;
-  const char* names[2] = {"2-CTA SS  A=K-major B=K-major  M=256 N=128", "2-CTA TS  A=TMEM    B=K-major  M=256 N=128"};
-  for (int cs = 0; cs < 2; ++cs) {
-    Args2 a{cs == 0 ? 0 : 2};
+  const char* names[4] = {"2-CTA SS  A=K-major B=K-major  M=256 N=128", "2-CTA TS  A=TMEM    B=K-major  M=256 N=128",
+                          "2-CTA SS  + leader-barrier TMA / remote arrives", "2-CTA TS  + leader-barrier TMA / remote arrives"};
+  for (int cs = 0; cs < 4; ++cs) {
+    Args2 a{(cs & 1) == 0 ? 0 : 2, cs >> 1};
     CK(cudaMemset(dD, 0xff, M * N * 4));
     probe2_kernel<<<2, 128, 56 * 1024>>>(tmA, tmB, dA, dD, a);
     cudaError_t e = cudaDeviceSynchronize();
