@@ -18,3 +18,8 @@ from .utils import (  # noqa: F401,E402
     correct_attn_out_lse_with_sink,
     correct_attn_out_with_sink,
 )
+
+try:  # registers torch.ops.flex_flash_attn.* (the reference's torch.compile seam); skipped if the namespace already has them
+    from . import custom_ops  # noqa: F401,E402
+except RuntimeError:  # pragma: no cover - the ops were registered by another library in this process
+    custom_ops = None

@@ -137,3 +137,45 @@ def test_no_oracle_import_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(d, f)).read()
                 assert "oracle" not in src, f"{f} references the oracle"
+
+
+def test_torch_custom_op_seam_matches_reference_schema():
+    """torch.ops.flex_flash_attn._flex_flash_attn_{forward,backward}_compilable exist with the reference's argument names
+    (functional/flex_flash_attn.py:193-330, 462-590), are mutable (in-place) ops, have fake impls and no CPU kernel."""
+    import torch
+    import magiattention_b200.functional  # noqa: F401  (registers the ops)
+
+    fwd = torch.ops.flex_flash_attn._flex_flash_attn_forward_compilable.default
+    bwd = torch.ops.flex_flash_attn._flex_flash_attn_backward_compilable.default
+    assert [a.name for a in fwd._schema.arguments] == [
+        "q", "k", "v", "sink", "sink_layout", "out_", "lse", "q_ranges", "k_ranges", "attn_type_map", "softmax_scale", "softcap",
+        "out_type", "disable_fwd_atomic_reduction", "deterministic", "sm_margin", "kblock_m", "kblock_n", "max_seqlen_q",
+        "auto_range_merge", "merge_q_ranges", "fwd_qk_map", "fwd_unique_count", "swap_ab", "pack_gqa", "sparse_load",
+        "sparse_load_loop_count", "sparse_load_invalid_count", "equal_k_range_size", "index_attn", "index_attn_indices_2d",
+        "index_attn_max_topk", "return_max_logits", "max_logits"]
+    assert [a.name for a in bwd._schema.arguments] == [
+        "dout", "q", "k", "v", "sink", "sink_layout", "out_", "lse", "dq", "dk", "dv", "dsink", "q_ranges", "k_ranges",
+        "attn_type_map", "softmax_scale", "softcap", "dq_type", "dk_type", "dv_type", "disable_bwd_dkv_atomic_reduction",
+        "deterministic", "sm_margin", "auto_range_merge", "merge_k_ranges", "bwd_kq_map", "bwd_unique_count", "swap_bwd_qk_loop",
+        "pack_gqa", "cat_gqa"]
+    assert {a.name for a in fwd._schema.arguments if a.alias_info and a.alias_info.is_write} == {"out_", "lse", "max_logits"}
+    assert {a.name for a in bwd._schema.arguments if a.alias_info and a.alias_info.is_write} == {"dq", "dk", "dv", "dsink"}
+    # traceable: under fake tensors the op is a no-op that returns None
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    with FakeTensorMode():
+        q = torch.empty(64, 2, 128, dtype=torch.bfloat16, device="cuda")
+        out = torch.empty(64, 2, 128, dtype=torch.float32, device="cuda")
+        lse = torch.empty(64, 2, dtype=torch.float32, device="cuda")
+        r = torch.empty(1, 2, dtype=torch.int32, device="cuda")
+        res = torch.ops.flex_flash_attn._flex_flash_attn_forward_compilable(
+            q, q, q, None, "sh", out, lse, r, r, None, 0.1, 0.0, None, False, False, 0, None, None, None, False, None, None, None,
+            False, False, False, None, None, None, False, None, 0, False, None)
+        assert res is None
+    # no host kernel: the op refuses CPU tensors instead of computing anything
+    qc = torch.zeros(64, 2, 128, dtype=torch.bfloat16)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.flex_flash_attn._flex_flash_attn_forward_compilable(
+            qc, qc, qc, None, "sh", qc.float(), torch.zeros(64, 2), torch.zeros(1, 2, dtype=torch.int32),
+            torch.zeros(1, 2, dtype=torch.int32), None, 0.1, 0.0, None, False, False, 0, None, None, None, False, None, None, None,
+            False, False, False, None, None, None, False, None, 0, False, None)

@@ -209,6 +209,43 @@ def test_correct_attn_out_lse_kernels():
             torch.testing.assert_close(l3.double(), sl, atol=1e-5, rtol=1e-5)
 
 
+def test_torch_custom_ops_equal_eager_path():
+    """torch.ops.flex_flash_attn._flex_flash_attn_{forward,backward}_compilable (the reference's torch.compile seam,
+    functional/custom_ops.py) give the same results as the eager launchers: fresh (0, -inf) / zero buffers in, merged results out."""
+    import magiattention_b200.functional  # noqa: F401  (registers the ops)
+    from magiattention_b200.functional.flex_flash_attn import _flex_flash_attn_backward, _flex_flash_attn_forward
+
+    dev = _dev()
+    torch.manual_seed(4)
+    T, HQ, HK = 300, 2, 1
+    q, do = (torch.randn(T, HQ, D, dtype=torch.bfloat16, device=dev) for _ in range(2))
+    k, v = (torch.randn(T, HK, D, dtype=torch.bfloat16, device=dev) for _ in range(2))
+    qr = torch.tensor([[0, 200], [200, 300]], dtype=torch.int32, device=dev)
+    kr = torch.tensor([[0, 200], [50, 300]], dtype=torch.int32, device=dev)
+    ty = torch.tensor([1, 0], dtype=torch.int32, device=dev)
+    sc = D ** -0.5
+    o_ref, m_ref = _flex_flash_attn_forward(q, k, v, None, "sh", None, None, qr, kr, ty, sc, 0.0, torch.float32)
+    out = torch.zeros(T, HQ, D, dtype=torch.float32, device=dev)
+    lse = torch.full((T, HQ), float("-inf"), dtype=torch.float32, device=dev)
+    res = torch.ops.flex_flash_attn._flex_flash_attn_forward_compilable(
+        q, k, v, None, "sh", out, lse, qr, kr, ty, sc, 0.0, None, False, False, 0, None, None, None, False, None, None, None,
+        False, False, False, None, None, None, False, None, 0, False, None)
+    assert res is None
+    torch.testing.assert_close(out, o_ref, atol=1e-6, rtol=1e-6)
+    torch.testing.assert_close(lse, m_ref.lse, atol=1e-6, rtol=1e-6)
+    dq_ref, dk_ref, dv_ref, _ = _flex_flash_attn_backward(do, q, k, v, None, "sh", o_ref, m_ref.lse, None, None, None, None, qr, kr, ty,
+                                                          sc, 0.0)
+    dq = torch.zeros(T, HQ, D, dtype=torch.float32, device=dev)
+    dk, dv = (torch.zeros(T, HK, D, dtype=torch.float32, device=dev) for _ in range(2))
+    torch.ops.flex_flash_attn._flex_flash_attn_backward_compilable(
+        do, q, k, v, None, "sh", out, lse, dq, dk, dv, None, qr, kr, ty, sc, 0.0, None, None, None, False, False, 0, False, None, None,
+        None, False, False, False)
+    # dq goes through an fp32 reduce-add whose order is not fixed: equal up to fp32 rounding; dk / dv are deterministic
+    torch.testing.assert_close(dq, dq_ref, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(dk, dk_ref, atol=1e-6, rtol=1e-6)
+    torch.testing.assert_close(dv, dv_ref, atol=1e-6, rtol=1e-6)
+
+
 def test_max_logits_accumulates_across_calls():
     """A given max_logits buffer is max-reduced into (the CP runtime passes one buffer through every stage)."""
     from magiattention_b200.functional.flex_flash_attn import _flex_flash_attn_forward
