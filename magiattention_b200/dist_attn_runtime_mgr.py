@@ -91,8 +91,9 @@ class DistAttnRuntimeMgr:
         self.comm_meta, self.calc_meta = comm_metas[self.cp_rank], calc_metas[self.cp_rank]
         self.all_calc_metas = calc_metas  # kept for FLOP / balance accounting
         self.all_comm_metas = comm_metas
-        self.dist_attn_runtime = DistAttnRuntime(self.comm_meta, self.calc_meta, cp_group,
-                                                 high_precision_reduce=key.config.high_precision_reduce,
+        # fp32 wire dtype for the partial dK/dV reduce: config field, or the reference's env switch (env/comm.py:107-121)
+        hp_reduce = key.config.high_precision_reduce or os.environ.get("MAGI_ATTENTION_BACKWARD_HIGH_PRECISION_REDUCE", "0") == "1"
+        self.dist_attn_runtime = DistAttnRuntime(self.comm_meta, self.calc_meta, cp_group, high_precision_reduce=hp_reduce,
                                                  all_comm_metas=comm_metas)
         self._position_ids: torch.Tensor | None = None
 
