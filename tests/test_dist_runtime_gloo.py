@@ -52,7 +52,7 @@ def _install_fake_kernels():
     _lib.ffa_bwd = fake_lib_bwd
 
 
-def _runtime_body(rank, world, name, degree, alg=None):
+def _runtime_body(rank, world, name, degree, alg=None, hp_reduce=False):
     from magiattention_b200.api import calc_attn, compute_pad_size, dispatch, magi_attn_flex_key, undispatch
     from magiattention_b200.common import AttnRanges
     from magiattention_b200.config import DispatchConfig, DistAttnConfig, OverlapConfig
@@ -70,7 +70,7 @@ def _runtime_body(rank, world, name, degree, alg=None):
                              H, HK, D, pad, dist.group.WORLD,
                              dist_attn_config=DistAttnConfig(
                                  dispatch_config=DispatchConfig(alg=alg) if alg is not None else DispatchConfig(),
-                                 overlap_config=OverlapConfig(True, degree)), chunk_size=chunk)
+                                 overlap_config=OverlapConfig(True, degree), high_precision_reduce=hp_reduce), chunk_size=chunk)
     ol, meta = calc_attn(dispatch(q, key), dispatch(k, key), dispatch(v, key), key)
     out = undispatch(ol, key)
     out.backward(do)
@@ -224,3 +224,9 @@ def _roll_body(rank, world):
 @pytest.mark.parametrize("world", [2, 4])
 def test_roll_gloo(world):
     _run(world, _roll_body)
+
+
+def test_cp_runtime_fp32_wire_for_dkv_gloo():
+    """high_precision_reduce: the partial dK/dV of every stage travel as fp32 (reference env switch
+    MAGI_ATTENTION_BACKWARD_HIGH_PRECISION_REDUCE / our DistAttnConfig field)."""
+    _run(4, _runtime_body, "sliding_window_causal", 2, None, True)
