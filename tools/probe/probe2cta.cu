@@ -9,6 +9,7 @@
 // Case 2 repeats the product with A taken from TMEM (the P / dS^T operand form of the attention kernels).
 // Cases 3-4 (added after the hardware run, NOT YET RUN) repeat both with the barrier protocol of csrc/ffa_fwd2.cu: cta_group::2 TMA
 // loads completing on the leader's mbarrier (mapa) and 256 local + remote thread arrivals gating the leader's MMA.
+// A last, informational step runs an M = 128 pair MMA (64 rows per CTA) and prints where D lands in each CTA's TMEM.
 // Cases 1-2 validated on a B200 (profiles/r01_probe2cta.txt): both pass — the B operand really is split across the pair by N halves
 // at the same shared-memory offset in both CTAs, and the TMEM-A form works with each CTA's own TMEM rows.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o tools/probe/probe2cta tools/probe/probe2cta.cu -lcuda
@@ -164,6 +165,80 @@ probe2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (wid == 0) tmem_dealloc2(tmem, 256);
 }
 
+// ---- layout discovery: cta_group::2 with M = 128 (64 rows of A / D per CTA), N = 128 --------------------------------------
+// D[128 x 128] = A[128 x 128] * B[128 x 128]^T; CTA r holds A rows [64r, 64r+64) and B rows [64r, 64r+64).  Every thread dumps its
+// whole TMEM lane (128 columns) so the host can print where each D element landed (needed by the paired-dQ backward).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+probe2_m128_kernel(const __grid_constant__ CUtensorMap tmA64, const __grid_constant__ CUtensorMap tmB, float* __restrict__ dump) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;          // 64 rows x 128 K: 2 boxes [64 rows][64 cols] of 8 KB
+  uint8_t* sB = smem + 16384;  // 64 rows x 128 K
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 32768 + 64);
+  const uint32_t bar_tma = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+  const int tid = threadIdx.x, wid = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  if (tid == 0) {
+    mbar_init(bar_tma, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (wid == 0) {
+    tmem_alloc2(smem_u32(tmem_slot), 128);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // poison the accumulator so untouched TMEM cells are recognisable (0xffc00000 = NaN)
+  {
+    uint32_t r[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = 0xffc00000u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) tmem_st32(tmem + (uint32_t(wid * 32) << 16) + c * 32, r);
+    tc_wait_st();
+  }
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_tma, 32768);
+    tma_load_2d(smem_u32(sA), &tmA64, bar_tma, 0, int(rank) * 64);
+    tma_load_2d(smem_u32(sA + 8192), &tmA64, bar_tma, 64, int(rank) * 64);
+    tma_load_2d(smem_u32(sB), &tmB, bar_tma, 0, int(rank) * 64);
+    tma_load_2d(smem_u32(sB + 8192), &tmB, bar_tma, 64, int(rank) * 64);
+  }
+  mbar_wait(bar_tma, 0);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  if (rank == 0 && wid == 0) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc(true, false, false, 128, 128);
+#pragma unroll 1
+      for (uint32_t k = 0; k < 8; ++k) {
+        const uint32_t off = (k >> 2) * 8192 + (k & 3) * 32;
+        mma2_ss(tmem, smem_desc(DESC_KMAJOR, smem_u32(sA) + off), smem_desc(DESC_KMAJOR, smem_u32(sB) + off), idesc, k > 0);
+      }
+      tc_commit2(bar_mma, 0x3);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar_mma, 0);
+  tc_fence_after();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32];
+    tmem_ld32(tmem + (uint32_t(wid * 32) << 16) + c * 32, r);
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dump[(size_t(rank) * 128 + tid) * 128 + c * 32 + i] = __uint_as_float(r[i]);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (wid == 0) tmem_dealloc2(tmem, 128);
+}
+
 static float bf2f(__nv_bfloat16 x) { return __bfloat162float(x); }
 
 int main() {
@@ -227,6 +302,50 @@ int main() {
     bool ok = maxerr < 1e-2;
     n_fail += !ok;
     printf("[%s] %-48s : max|err| = %.3e (max|ref| = %.2f)\n", ok ? "PASS" : "FAIL", names[cs], maxerr, maxref);
+  }
+  {
+    // M = 128 pair accumulator: where does D[m][n] live?  (informational; not counted as pass / fail)
+    CUtensorMap tmA64 = make_map(dA, M, 64);  // rows 0..127 of A are used
+    CK(cudaFuncSetAttribute(probe2_m128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024));
+    float* dDump;
+    CK(cudaMalloc(&dDump, 2 * 128 * 128 * 4));
+    CK(cudaMemset(dDump, 0, 2 * 128 * 128 * 4));
+    probe2_m128_kernel<<<2, 128, 40 * 1024>>>(tmA64, tmB, dDump);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("[INFO] M=128 pair layout probe: launch error %s\n", cudaGetErrorString(e));
+      return 3;
+    }
+    std::vector<float> hDump(2 * 128 * 128), ref(128 * 128);
+    CK(cudaMemcpy(hDump.data(), dDump, hDump.size() * 4, cudaMemcpyDeviceToHost));
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < 128; ++n) {
+        float acc = 0;
+        for (int k = 0; k < K; ++k) acc += bf2f(hA[m * K + k]) * bf2f(hB[n * K + k]);
+        ref[m * 128 + n] = acc;
+      }
+    auto find = [&](float v, int& m, int& n) {
+      if (!(v == v)) return false;  // NaN poison: never written
+      for (m = 0; m < 128; ++m)
+        for (n = 0; n < 128; ++n)
+          if (fabs(ref[m * 128 + n] - v) < 2e-3 * (1.0 + fabs(v))) return true;
+      return false;
+    };
+    const int lanes[] = {0, 1, 15, 16, 31, 32, 47, 63, 64, 65, 95, 127}, cols[] = {0, 1, 31, 32, 63, 64, 65, 127};
+    for (int r = 0; r < 2; ++r) {
+      int written = 0;
+      for (int i = 0; i < 128 * 128; ++i) written += hDump[(size_t(r) * 128) * 128 + i] == hDump[(size_t(r) * 128) * 128 + i];
+      printf("[INFO] M=128 pair accumulator, CTA %d: %d of 16384 TMEM cells written; (lane, col) -> D(m, n):\n", r, written);
+      for (int l : lanes) {
+        printf("   lane %3d:", l);
+        for (int c : cols) {
+          int m, n;
+          if (find(hDump[(size_t(r) * 128 + l) * 128 + c], m, n)) printf("  c%-3d->(%3d,%3d)", c, m, n);
+          else printf("  c%-3d->   --    ", c);
+        }
+        printf("\n");
+      }
+    }
   }
   printf("probe2cta done: %d failing cases\n", n_fail);
   return n_fail ? 1 : 0;
