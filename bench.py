@@ -360,6 +360,8 @@ def main():
     e2e = None
     if not a.no_e2e:
         NCH = (8 if world == 1 else 2) if H % 8 == 0 else 1  # fewer, larger chunks under CP (per-call comm overhead)
+        NCH = int(os.environ.get("B200_BENCH_E2E_CHUNKS", NCH))  # tuning knob; must divide the head count
+        assert H % NCH == 0
         Hc = H // NCH
         host_in = [[x[:, c * Hc:(c + 1) * Hc].contiguous().pin_memory() for c in range(NCH)] for x in (hq, hk, hv, hdo)]
         host_out = [[torch.empty(S_local, Hc, D, dtype=torch.bfloat16).pin_memory() for _ in range(NCH)] for _ in range(4)]
