@@ -47,6 +47,8 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap,
 
 struct Args2 {
   int a_src;     // 0 = A from shared memory (SS), 2 = A from TMEM (TS)
+  int b_mn;      // 0 = B K-major [N][K], split by N rows (the K operand of S = Q K^T); 1 = B MN-major [K][N], split by N column
+                 // halves: CTA r holds columns [64r, 64r+64) of all 128 K rows (the V operand of O = P V in csrc/ffa_fwd2.cu)
   int protocol;  // 0 = every CTA waits its own TMA barrier, then a cluster barrier (validated);
                  // 1 = the barrier protocol of csrc/ffa_fwd2.cu: all TMA loads of the pair complete on the LEADER's mbarrier
                  //     (cp.async.bulk.tensor.cta_group::2 + mapa), and the leader's MMA is additionally gated by an mbarrier that
@@ -55,7 +57,7 @@ struct Args2 {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
 probe2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-              const __nv_bfloat16* __restrict__ Ag, float* __restrict__ D, Args2 args) {
+              const __grid_constant__ CUtensorMap tmBmn, const __nv_bfloat16* __restrict__ Ag, float* __restrict__ D, Args2 args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;          // 128 rows x 128 K: 2 boxes [128 rows][64 cols] of 16 KB
@@ -92,8 +94,12 @@ probe2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tma_load_2d(smem_u32(sA), &tmA, bar_tma, 0, int(rank) * 128);
         tma_load_2d(smem_u32(sA + 16384), &tmA, bar_tma, 64, int(rank) * 128);
       }
-      tma_load_2d(smem_u32(sB), &tmB, bar_tma, 0, int(rank) * 64);
-      tma_load_2d(smem_u32(sB + 8192), &tmB, bar_tma, 64, int(rank) * 64);
+      if (args.b_mn) {
+        tma_load_2d(smem_u32(sB), &tmBmn, bar_tma, int(rank) * 64, 0);  // [128 K rows][64 N cols]: 16 KB
+      } else {
+        tma_load_2d(smem_u32(sB), &tmB, bar_tma, 0, int(rank) * 64);
+        tma_load_2d(smem_u32(sB + 8192), &tmB, bar_tma, 64, int(rank) * 64);
+      }
     } else {
       const uint32_t leader_bar = mapa_shared(bar_tma, 0);
       if (rank == 0) mbar_arrive_expect_tx(bar_tma, 2 * my_bytes);  // both CTAs' bytes land on the leader's barrier
@@ -101,8 +107,12 @@ probe2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tma_load_2d_pair(smem_u32(sA), &tmA, leader_bar, 0, int(rank) * 128);
         tma_load_2d_pair(smem_u32(sA + 16384), &tmA, leader_bar, 64, int(rank) * 128);
       }
-      tma_load_2d_pair(smem_u32(sB), &tmB, leader_bar, 0, int(rank) * 64);
-      tma_load_2d_pair(smem_u32(sB + 8192), &tmB, leader_bar, 64, int(rank) * 64);
+      if (args.b_mn) {
+        tma_load_2d_pair(smem_u32(sB), &tmBmn, leader_bar, int(rank) * 64, 0);
+      } else {
+        tma_load_2d_pair(smem_u32(sB), &tmB, leader_bar, 0, int(rank) * 64);
+        tma_load_2d_pair(smem_u32(sB + 8192), &tmB, leader_bar, 64, int(rank) * 64);
+      }
     }
   }
   if (args.a_src == 2) {
@@ -135,10 +145,11 @@ probe2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tc_fence_after();
     }
     if (elect_one()) {
-      const uint32_t idesc = make_idesc(true, false, false, 256, 128);
+      const uint32_t idesc = make_idesc(true, false, args.b_mn != 0, 256, 128);
 #pragma unroll 1
       for (uint32_t k = 0; k < 8; ++k) {
-        const uint64_t bd = smem_desc(DESC_KMAJOR, smem_u32(sB) + (k >> 2) * 8192 + (k & 3) * 32);
+        const uint64_t bd = args.b_mn ? smem_desc(desc_mnmajor(16384), smem_u32(sB) + k * 2048)  // 16 K rows per step
+                                      : smem_desc(DESC_KMAJOR, smem_u32(sB) + (k >> 2) * 8192 + (k & 3) * 32);
         if (args.a_src == 0) {
           const uint64_t ad = smem_desc(DESC_KMAJOR, smem_u32(sA) + (k >> 2) * 16384 + (k & 3) * 32);
           mma2_ss(tmem, ad, bd, idesc, k > 0);
@@ -273,15 +284,16 @@ int main() {
     }
     return m;
   };
-  CUtensorMap tmA = make_map(dA, M, 128), tmB = make_map(dB, N, 64);
+  CUtensorMap tmA = make_map(dA, M, 128), tmB = make_map(dB, N, 64), tmBmn = make_map(dB, N, 128);
   CK(cudaFuncSetAttribute(probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024));
   int n_fail = 0;
-  const char* names[4] = {"2-CTA SS  A=K-major B=K-major  M=256 N=128", "2-CTA TS  A=TMEM    B=K-major  M=256 N=128",
-                          "2-CTA SS  + leader-barrier TMA / remote arrives", "2-CTA TS  + leader-barrier TMA / remote arrives"};
-  for (int cs = 0; cs < 4; ++cs) {
-    Args2 a{(cs & 1) == 0 ? 0 : 2, cs >> 1};
+  const char* names[6] = {"2-CTA SS  A=K-major B=K-major  M=256 N=128", "2-CTA TS  A=TMEM    B=K-major  M=256 N=128",
+                          "2-CTA SS  + leader-barrier TMA / remote arrives", "2-CTA TS  + leader-barrier TMA / remote arrives",
+                          "2-CTA SS  B=MN-major split by N column halves", "2-CTA TS  B=MN-major split by N column halves (PV)"};
+  for (int cs = 0; cs < 6; ++cs) {
+    Args2 a{(cs & 1) == 0 ? 0 : 2, cs >= 4 ? 1 : 0, (cs >> 1) == 1 ? 1 : 0};
     CK(cudaMemset(dD, 0xff, M * N * 4));
-    probe2_kernel<<<2, 128, 56 * 1024>>>(tmA, tmB, dA, dD, a);
+    probe2_kernel<<<2, 128, 56 * 1024>>>(tmA, tmB, tmBmn, dA, dD, a);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
       printf("[FAIL] %-48s : launch error %s\n", names[cs], cudaGetErrorString(e));
@@ -293,7 +305,7 @@ int main() {
     for (int m = 0; m < M; ++m)
       for (int n = 0; n < N; ++n) {
         float acc = 0;
-        for (int k = 0; k < K; ++k) acc += bf2f(hA[m * K + k]) * bf2f(hB[n * K + k]);
+        for (int k = 0; k < K; ++k) acc += bf2f(hA[m * K + k]) * (a.b_mn ? bf2f(hB[k * N + n]) : bf2f(hB[n * K + k]));
         double err = fabs(double(acc) - double(hD[m * N + n]));
         if (!(err <= 1e30)) err = 1e30;
         maxerr = fmax(maxerr, err);
