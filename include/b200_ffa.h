@@ -182,6 +182,31 @@ B200_API int b200_range_reduce_sum(void* dst, int32_t dst_dtype, const void* src
                           const int32_t* dst_ranges, const int32_t* src_ranges, int32_t num_ranges,
                           int64_t row_elems, b200_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * NVLink peer-memory exchange primitives — the engine under group_cast / group_reduce for ranks of one NVSwitch
+ * domain.  They replace the reference's a2av group collective (magi_attention/comm/primitive/grpcoll/
+ * _a2av_grpcoll_impl.py:69-179 group_cast, :228-340 group_reduce; all_to_all_v _all2all_v.py:52-111 and the
+ * range_gather / range_reduce passes around it): rows move with copy engines between IPC-mapped arenas, ordering is
+ * by 32-bit epoch flags in the arenas.  All calls enqueue on `stream` (except alloc/free/export/import, which are
+ * synchronous set-up calls) and return 0 or a negative b200_status.
+ * --------------------------------------------------------------------------------------------------------- */
+/* cudaMalloc'd, zero-filled arena (IPC-exportable).  Synchronous. */
+B200_API int b200_nvl_alloc(void** ptr, size_t bytes);
+B200_API int b200_nvl_free(void* ptr);
+/* 64-byte IPC handle of an arena / mapping of a peer's arena into this process (lazy peer access). */
+B200_API int b200_nvl_export(const void* ptr, uint8_t handle[64]);
+B200_API int b200_nvl_import(const uint8_t handle[64], void** ptr);
+B200_API int b200_nvl_release(void* ptr);
+/* n device-to-device copies dst[i] <- src[i] (bytes[i] each; local or peer-mapped pointers) on the copy engines. */
+B200_API int b200_nvl_copy_spans(int32_t n, void* const* dst, const void* const* src, const size_t* bytes,
+                                 b200_stream_t stream);
+/* After all earlier work of `stream`: *flags[i] = value for i < n (n <= 64; flags may live in peers' arenas). */
+B200_API int b200_nvl_signal(void* const* flags, int32_t n, uint32_t value, b200_stream_t stream);
+/* Hold `stream` until every *flags[i] >= value (wrap-safe signed difference).  After timeout_ns the wait gives up and
+ * sets *err = 1 (err: device-accessible, e.g. pinned host memory) so that a protocol error cannot hang the GPU. */
+B200_API int b200_nvl_wait(void* const* flags, int32_t n, uint32_t value, uint32_t* err, uint64_t timeout_ns,
+                           b200_stream_t stream);
+
 /* Number of kernels the last b200_ffa_fwd / b200_ffa_bwd call on this thread launched (for bench accounting). */
 B200_API int b200_ffa_last_launch_count(void);
 

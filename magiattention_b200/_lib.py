@@ -72,6 +72,8 @@ class BwdParams(C.Structure):
 EXPORTS = [
     "b200_ffa_version", "b200_ffa_last_error", "b200_ffa_fwd_workspace_bytes", "b200_ffa_bwd_workspace_bytes",
     "b200_ffa_fwd", "b200_ffa_bwd", "b200_lse_merge", "b200_sink_merge", "b200_range_reduce_sum", "b200_ffa_last_launch_count",
+    "b200_nvl_alloc", "b200_nvl_free", "b200_nvl_export", "b200_nvl_import", "b200_nvl_release", "b200_nvl_copy_spans",
+    "b200_nvl_signal", "b200_nvl_wait",
 ]
 
 _lib = None
@@ -110,6 +112,23 @@ def lib() -> C.CDLL:
                 l.b200_range_reduce_sum.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                                     C.c_int32, C.c_int64, C.c_void_p]
                 l.b200_ffa_last_launch_count.restype = C.c_int
+                l.b200_nvl_alloc.restype = C.c_int
+                l.b200_nvl_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+                l.b200_nvl_free.restype = C.c_int
+                l.b200_nvl_free.argtypes = [C.c_void_p]
+                l.b200_nvl_export.restype = C.c_int
+                l.b200_nvl_export.argtypes = [C.c_void_p, C.c_char_p]
+                l.b200_nvl_import.restype = C.c_int
+                l.b200_nvl_import.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+                l.b200_nvl_release.restype = C.c_int
+                l.b200_nvl_release.argtypes = [C.c_void_p]
+                l.b200_nvl_copy_spans.restype = C.c_int
+                l.b200_nvl_copy_spans.argtypes = [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                  C.POINTER(C.c_size_t), C.c_void_p]
+                l.b200_nvl_signal.restype = C.c_int
+                l.b200_nvl_signal.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_uint32, C.c_void_p]
+                l.b200_nvl_wait.restype = C.c_int
+                l.b200_nvl_wait.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
                 _lib = l
     return _lib
 
@@ -289,3 +308,64 @@ def range_reduce_sum(dst: torch.Tensor, src: torch.Tensor, dst_ranges: torch.Ten
     _check(l.b200_range_reduce_sum(dst.data_ptr(), _DT[dst.dtype], src.data_ptr(), _DT[src.dtype],
                                    dst_ranges.data_ptr(), src_ranges.data_ptr(), int(dst_ranges.shape[0]), row_elems,
                                    _stream_ptr(dst.device)), "b200_range_reduce_sum")
+
+
+# ---- NVLink peer-memory exchange primitives (csrc/nvl_exchange.cu) -----------------------------------------
+def nvl_alloc(nbytes: int) -> int:
+    """Zero-filled cudaMalloc'd arena on the current device (IPC-exportable); returns the device pointer."""
+    p = C.c_void_p()
+    _check(lib().b200_nvl_alloc(C.byref(p), nbytes), "b200_nvl_alloc")
+    return int(p.value)
+
+
+def nvl_free(ptr: int) -> None:
+    _check(lib().b200_nvl_free(ptr), "b200_nvl_free")
+
+
+def nvl_export(ptr: int) -> bytes:
+    buf = C.create_string_buffer(64)
+    _check(lib().b200_nvl_export(ptr, buf), "b200_nvl_export")
+    return buf.raw
+
+
+def nvl_import(handle: bytes) -> int:
+    p = C.c_void_p()
+    _check(lib().b200_nvl_import(C.create_string_buffer(handle, 64), C.byref(p)), "b200_nvl_import")
+    return int(p.value)
+
+
+def nvl_release(ptr: int) -> None:
+    _check(lib().b200_nvl_release(ptr), "b200_nvl_release")
+
+
+class NvlCopyList:
+    """A reusable (dst, src, bytes) span table marshalled once for b200_nvl_copy_spans."""
+
+    def __init__(self, spans: list[tuple[int, int, int]]):
+        n = len(spans)
+        self.n = n
+        self.dst = (C.c_void_p * max(n, 1))(*[s[0] for s in spans])
+        self.src = (C.c_void_p * max(n, 1))(*[s[1] for s in spans])
+        self.nbytes = (C.c_size_t * max(n, 1))(*[s[2] for s in spans])
+        self.total = sum(s[2] for s in spans)
+
+    def launch(self, stream: int) -> None:
+        if self.n:
+            _check(lib().b200_nvl_copy_spans(self.n, self.dst, self.src, self.nbytes, stream), "b200_nvl_copy_spans")
+
+
+class NvlFlagList:
+    """A reusable list of flag addresses for b200_nvl_signal / b200_nvl_wait (<= 64)."""
+
+    def __init__(self, addrs: list[int]):
+        assert len(addrs) <= 64
+        self.n = len(addrs)
+        self.arr = (C.c_void_p * max(self.n, 1))(*addrs)
+
+    def signal(self, value: int, stream: int) -> None:
+        if self.n:
+            _check(lib().b200_nvl_signal(self.arr, self.n, value & 0xFFFFFFFF, stream), "b200_nvl_signal")
+
+    def wait(self, value: int, err_ptr: int, timeout_ns: int, stream: int) -> None:
+        if self.n:
+            _check(lib().b200_nvl_wait(self.arr, self.n, value & 0xFFFFFFFF, err_ptr, timeout_ns, stream), "b200_nvl_wait")

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200_ffa.so")
-SOURCES = ["ffa_api.cu", "ffa_plan.cu", "ffa_fwd.cu", "ffa_fwd64.cu", "ffa_fwd2.cu", "ffa_bwd.cu", "ffa_aux.cu"]
+SOURCES = ["ffa_api.cu", "ffa_plan.cu", "ffa_fwd.cu", "ffa_bwd.cu", "ffa_aux.cu", "nvl_exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -8,9 +8,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#ifndef FFA_FWD_DEFAULT_VARIANT
-#define FFA_FWD_DEFAULT_VARIANT 128
-#endif
 #include "../../include/b200_ffa.h"
 #include "ffa_args.h"
 #include "ffa_kernels.h"
@@ -32,15 +29,15 @@ typedef CUresult (*EncodeTiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+EncodeTiled_t resolve_encode() {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+  return (EncodeTiled_t)p;
+}
+
 EncodeTiled_t get_encode() {
-  static EncodeTiled_t fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiled_t)p;
-  }
+  static EncodeTiled_t fn = resolve_encode();  // function-local static: thread-safe one-time initialisation
   return fn;
 }
 
@@ -77,18 +74,6 @@ int make_map_f32_acc(CUtensorMap* m, void* ptr, int head_dim, int tokens, int he
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-// forward kernel variant: 128 (default: 128-column kv blocks, ffa_fwd.cu), 64 (B200_FFA_FWD_VARIANT=64: 64-column kv blocks
-// with a double-buffered S, ffa_fwd64.cu — measured slower) or 2 (B200_FFA_FWD_VARIANT=2: CTA-pair cta_group::2 kernel,
-// ffa_fwd2.cu — EXPERIMENTAL, not yet run on hardware).  64 and 2: head_dim 128 only, no max_logits.
-int fwd_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200_FFA_FWD_VARIANT");
-    v = (e && atoi(e) == 128) ? 128 : (e && atoi(e) == 64) ? 64 : (e && atoi(e) == 2) ? 2 : FFA_FWD_DEFAULT_VARIANT;
-  }
-  return v;
-}
 
 int check_common(int dtype, int hq, int hk, int d, float softcap) {
   if (dtype != B200_F16 && dtype != B200_BF16) return fail(B200_ERR_INVALID, "dtype must be f16 or bf16");
@@ -148,11 +133,7 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   int* plan = static_cast<int*>(p->workspace);
   const size_t cap_bytes = p->workspace_bytes - ffa::plan_entries_off(n_tiles) * sizeof(int);
   const int capacity = int(cap_bytes / sizeof(int) > 0x7fffffff ? 0x7fffffff : cap_bytes / sizeof(int));
-  const bool use_fwd64 = fwd_variant() == 64 && p->head_dim == 128 && !p->max_logits;
-  const bool use_pair = fwd_variant() == 2 && p->head_dim == 128 && !p->max_logits;
-  // the CTA-pair kernel walks one slice list per 512 q rows (the offsets / entries fit the same workspace)
-  cudaError_t e = use_pair ? ffa::launch_plan_fwd_rows(meta, (n_tiles + 1) / 2, 2 * ffa::kFwdTileQ, capacity, plan, stream)
-                           : ffa::launch_plan(true, meta, n_tiles, capacity, plan, stream);
+  cudaError_t e = ffa::launch_plan(true, meta, n_tiles, capacity, plan, stream);
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "plan launch: %s", cudaGetErrorString(e));
   ++g_launches;
 
@@ -160,8 +141,7 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   if (int rc = make_map_thd(&tmQ, p->q, p->dtype, p->head_dim, p->total_q, p->num_heads_q, p->q_stride_t, p->q_stride_h, 128, "q")) return rc;
   // k/v may legally be empty (total_k == 0): point the maps at q so encoding succeeds; no block is ever loaded.
   const bool kv_empty = p->total_k == 0;
-  // 64-row K boxes for the 64-column variant and for the pair kernel's K halves; V keeps 128-row boxes in the pair kernel
-  const int k_box_rows = (use_fwd64 || use_pair) ? 64 : 128, v_box_rows = use_fwd64 ? 64 : 128;
+  const int k_box_rows = 128, v_box_rows = 128;
   if (int rc = make_map_thd(&tmK, kv_empty ? p->q : p->k, p->dtype, p->head_dim, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
                             kv_empty ? p->q_stride_t : p->k_stride_t, kv_empty ? p->q_stride_h : p->k_stride_h, k_box_rows, "k")) return rc;
   if (int rc = make_map_thd(&tmV, kv_empty ? p->q : p->v, p->dtype, p->head_dim, kv_empty ? 1 : p->total_k, kv_empty ? p->num_heads_q : p->num_heads_kv,
@@ -184,11 +164,7 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   a.scale = p->softmax_scale;
   a.accumulate = p->accumulate;
   a.max_logits = p->max_logits;
-  e = use_pair
-          ? ffa::launch_fwd_pair(p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream)
-      : use_fwd64
-          ? ffa::launch_fwd64(p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream)
-          : ffa::launch_fwd(p->head_dim, p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream);
+  e = ffa::launch_fwd(p->head_dim, p->dtype == B200_BF16, p->out_dtype == B200_F32, tmQ, tmK, tmV, a, stream);
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "fwd launch: %s", cudaGetErrorString(e));
   ++g_launches;
   if (p->sink && p->seqlen_sink > 0) {

@@ -12,12 +12,6 @@ cudaError_t launch_plan(bool fwd, const SliceMeta& meta, int n_tiles, int capaci
 cudaError_t launch_plan_fwd_rows(const SliceMeta& meta, int n_tiles, int tile_rows, int capacity, int* plan, cudaStream_t stream);
 cudaError_t launch_fwd(int head_dim, bool bf16, bool out_f32, const CUtensorMap& tmQ, const CUtensorMap& tmK,
                        const CUtensorMap& tmV, const FwdArgs& a, cudaStream_t stream);
-// 64-column kv blocks, double-buffered S (K/V maps must use 64-row boxes)
-cudaError_t launch_fwd64(bool bf16, bool out_f32, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                         const FwdArgs& a, cudaStream_t stream);
-// EXPERIMENTAL CTA-pair forward (ffa_fwd2.cu): head_dim 128, plan over 512-row tiles, K map with 64-row boxes
-cudaError_t launch_fwd_pair(bool bf16, bool out_f32, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                            const FwdArgs& a, cudaStream_t stream);
 cudaError_t launch_bwd_preprocess(int head_dim, bool bf16, const void* out, const void* dout, const float* lse, float* delta,
                                   float* lse2, int total_q, int num_heads, int tq_ld, int64_t o_stride_t,
                                   int64_t o_stride_h, int64_t do_stride_t, int64_t do_stride_h, int64_t lse_stride_t,

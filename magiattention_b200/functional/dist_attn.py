@@ -12,11 +12,12 @@ DistAttnRuntime :141-2991, DistAttnFunc :2993-3605, dist_attn_func :3608-3680), 
             GLOBAL (out, lse) so partial grads are exact summands, then group_reduce the stage's partial
             dK,dV (16-bit wire dtype) back to their owners, asynchronously -> wait reduces -> cast.
 
-Communication and compute overlap because the compute kernels are non-persistent (one CTA per SM, short
-lived) and NCCL's stream is created high-priority (TORCH_NCCL_HIGH_PRIORITY=1, set by the runtime manager
-unless overridden): P2P CTAs are scheduled as attention CTAs retire, stage i+1 transfers hide behind stage
-i compute, and only the last stage's dKV reduce is exposed by construction (as in the reference,
-docs/source/blog/magi_attn.md:273-275).
+Communication and compute overlap stage by stage through CUDA events.  Default engine on one NVSwitch domain
+(comm/nvl_exchange.py): every transfer is a copy-engine pull over IPC-mapped peer memory on side streams, so no
+communication kernel takes an SM from the attention grid (``sm_margin`` is therefore unnecessary); ranks are
+ordered by epoch flags, not rendezvous.  Portable alternative (``MAGI_B200_KV_EXCHANGE=nccl``): grouped NCCL P2P
+on NCCL's high-priority stream.  In both, stage i+1 transfers hide behind stage i compute and only the last
+stage's dKV fold is exposed by construction (as in the reference, docs/source/blog/magi_attn.md:273-275).
 """
 from __future__ import annotations
 
@@ -35,8 +36,36 @@ from .flex_flash_attn import _flex_flash_attn_backward, _flex_flash_attn_forward
 __all__ = ["DistAttnRuntime", "DistAttnFunc", "dist_attn_func"]
 
 
+class _Ready:
+    """A finished 'work' around prefetched stage buffers (compute-only measurements)."""
+
+    def __init__(self, bufs):
+        self.bufs = bufs
+
+    def wait_post_process(self, *a, **k):
+        return self.bufs
+
+
+class _SendOnly:
+    """Stage in which this rank only sends: the transfer must be waited for, there is nothing to compute on."""
+
+    send_only = True
+
+    def __init__(self, work):
+        self.work = work
+
+    def wait_post_process(self, *a, **k):
+        self.work.wait_post_process()
+        return None
+
+
 class DistAttnRuntime:
-    """Holds the per-key metadata and implements the stage primitives (reference :141-239)."""
+    """Holds the per-key metadata and implements the stage primitives (reference :141-239).
+
+    Two exchange engines sit behind the same stage API:
+      * ``nvl``  (default on one NVSwitch domain): copy-engine pulls over IPC-mapped peer memory, comm/nvl_exchange.py;
+      * ``nccl`` (``MAGI_B200_KV_EXCHANGE=nccl``, or automatically when peer access is unavailable): group_cast /
+        group_reduce as grouped ncclSend/ncclRecv, comm/group_collective.py."""
 
     def __init__(self, comm_meta: CommMeta, calc_meta: CalcMeta, cp_group: dist.ProcessGroup | None,
                  sm_margin: int = 0, high_precision_reduce: bool = False, all_comm_metas: list[CommMeta] | None = None):
@@ -49,44 +78,95 @@ class DistAttnRuntime:
         self.cp_size = 1 if cp_group is None else dist.get_world_size(cp_group)
         # communication volume bookkeeping (rows of K == rows of V) for exposed-comm accounting
         self.remote_rows_per_stage = list(comm_meta.num_remote_kv_tokens_per_stage)
-        # opt-in experimental engine: KV pulled over NVLink peer memory instead of NCCL P2P (comm/peer_exchange.py)
         self.all_comm_metas = all_comm_metas
-        self._peer_fetchers: dict = {}
+        self.nvl = None
+        self._stub: list | None = None  # compute-only mode (bench exposed-comm A/B): prefetched stage buffers, no transfers
+        if self.cp_size > 1 and all_comm_metas is not None and cp_group is not None:
+            from ..comm.nvl_exchange import NvlKVExchange, nvl_available
+
+            if nvl_available(cp_group):  # collective: every rank builds its runtime for a key at the same point
+                self.nvl = NvlKVExchange(cp_group, all_comm_metas, self.overlap_degree, calc_meta.seqlen_k_local)
+
+    @property
+    def engine(self) -> str:
+        return "nvl" if self.nvl is not None else "nccl"
+
+    def _stage_idle(self, st: int) -> bool:
+        """True when this rank neither receives nor sends anything in stage ``st`` (decided from the transfer tables,
+        never from a fetch handle being None: an owner that consumes nothing still has to take part in the reduce)."""
+        arg = self.comm_meta.kv_group_collective_args_list[st]
+        return self.remote_rows_per_stage[st] == 0 and sum(map(len, arg.dst_indices_list)) == 0
 
     # ---- communication ---------------------------------------------------------------------------
-    def fetch_remote_kv(self, k: torch.Tensor, v: torch.Tensor) -> list[WorkWithPostProcessFn | None]:
-        """One async group_cast per stage, all issued now (reference: _fetch_remote_kv :1463-1567)."""
-        if os.environ.get("MAGI_B200_KV_EXCHANGE", "nccl") == "peer" and self.cp_size > 1 and self.all_comm_metas is not None:
-            return self._peer_fetcher(k).fetch(k, v)
+    def fetch_remote_kv(self, k: torch.Tensor, v: torch.Tensor, backward: bool = False) -> list[WorkWithPostProcessFn | None]:
+        """Start the exchange of one pass: one async work per stage, all issued now
+        (reference: _fetch_remote_kv :1463-1567).  A stage yields None when this rank receives no rows in it."""
+        if self._stub is not None:
+            return [_Ready(b) if b is not None else None for b in self._stub]
+        if self.nvl is not None:
+            return self.nvl.fetch(k, v, wire_esize=4 if self.high_precision_reduce else k.element_size(), backward=backward)
         works: list[WorkWithPostProcessFn | None] = []
         for st in range(self.overlap_degree):
-            if self.calc_meta.remote_attn_args_list[st].can_skip and self.remote_rows_per_stage[st] == 0 \
-                    and sum(map(len, self.comm_meta.kv_group_collective_args_list[st].dst_indices_list)) == 0:
+            if self._stage_idle(st):
                 works.append(None)
                 continue
             arg = self.comm_meta.kv_group_collective_args_list[st]
-            works.append(group_cast((k, v), None, group=self.cp_group, async_op=True, **arg.to_group_cast_args()))
+            w = group_cast((k, v), None, group=self.cp_group, async_op=True, **arg.to_group_cast_args())
+            if self.remote_rows_per_stage[st] == 0:  # send-only stage: keep the transfer alive, nothing to compute on
+                w = _SendOnly(w)
+            works.append(w)
         return works
 
-    def _peer_fetcher(self, k: torch.Tensor):
-        from ..comm.peer_exchange import PeerKVFetcher
+    def begin_reduce(self, dk: torch.Tensor, dv: torch.Tensor, wire: torch.dtype) -> None:
+        """Owner side of the dKV return path (nvl engine): enqueue, once per backward and after the local backward, the
+        pulls + folds of every stage on the reduce stream.  The NCCL engine reduces stage by stage instead."""
+        if self._stub is None and self.nvl is not None:
+            self.nvl.begin_reduce(dk, dv, wire)
 
-        key = (k.dtype, k.shape[1], k.shape[2], k.device)
-        f = self._peer_fetchers.get(key)
-        if f is None:  # collective: every rank builds it on its first fetch with this geometry
-            per_stage = [[cm.kv_group_collective_args_list[st] for cm in self.all_comm_metas] for st in range(self.overlap_degree)]
-            f = PeerKVFetcher(self.cp_group, dist.get_rank(self.cp_group), per_stage, k.shape[0], k.shape[1], k.shape[2], k.dtype,
-                              k.device)
-            self._peer_fetchers[key] = f
-        return f
+    def partial_buffers(self, st: int, rk: torch.Tensor, rv: torch.Tensor, wire: torch.dtype):
+        """Where the stage-``st`` backward kernel writes its partial dK,dV (wire dtype)."""
+        if self._stub is None and self.nvl is not None:
+            return self.nvl.partial_buffers(st, wire)
+        return torch.empty(rk.shape, dtype=wire, device=rk.device), torch.empty(rv.shape, dtype=wire, device=rv.device)
 
-    def reduce_partial_dkv(self, st: int, dk_part: torch.Tensor, dv_part: torch.Tensor, dk: torch.Tensor,
-                           dv: torch.Tensor) -> WorkWithPostProcessFn:
-        """Async group_reduce(sum) of a stage's partial dK,dV into the owners' fp32 dk/dv
-        (reference: _reduce_partial_dkv :2068-2195)."""
+    def reduce_partial_dkv(self, st: int, dk_part: torch.Tensor | None, dv_part: torch.Tensor | None, dk: torch.Tensor,
+                           dv: torch.Tensor, wire: torch.dtype | None = None) -> WorkWithPostProcessFn | None:
+        """Return a stage's partial dK,dV to their owners, summed into the owners' fp32 dk/dv
+        (reference: _reduce_partial_dkv :2068-2195).  nvl: signal the owners (they pull); nccl: async group_reduce."""
+        if self._stub is not None:
+            return None
+        if self.nvl is not None:
+            if dk_part is not None:
+                self.nvl.partial_ready(st)
+            return None
+        if self._stage_idle(st):
+            return None
         arg = self.comm_meta.kv_group_collective_args_list[st]
+        if dk_part is None:  # receive-only in the reduce (this rank consumed nothing of the stage): zero-row partials
+            wire = wire or dk.dtype  # the receive staging takes the partials' dtype: it must be the wire dtype
+            dk_part = torch.empty((0, *dk.shape[1:]), dtype=wire, device=dk.device)
+            dv_part = torch.empty((0, *dv.shape[1:]), dtype=wire, device=dv.device)
         return group_reduce((dk_part, dv_part), (dk, dv), group=self.cp_group, async_op=True, reduce_op="sum",
                             acc_reduce=True, **arg.to_group_reduce_args())
+
+    def finish_reduce(self, reduces: list) -> None:
+        for rw in reduces:
+            if rw is not None:
+                rw.wait_post_process()
+        if self._stub is None and self.nvl is not None:
+            self.nvl.finish_reduce()
+
+    def compute_only(self, stage_bufs: list | None):
+        """Context manager for measurements: run the same kernels on prefetched stage buffers with every transfer and
+        reduce stubbed out (the comm-disabled arm of the exposed-communication A/B)."""
+        rt = self
+
+        class _Ctx:
+            def __enter__(self_):
+                rt._stub = stage_bufs
+            def __exit__(self_, *a):
+                rt._stub = None
+        return _Ctx()
 
     def reduce_max_logits(self, max_logits: torch.Tensor | None) -> torch.Tensor | None:
         """Element-wise MAX over the cp group (reference: reduce_max_logits :532-555)."""
@@ -147,7 +227,10 @@ class DistAttnFunc(torch.autograd.Function):
             w = works[st]
             if w is None:
                 continue
-            rk, rv = w.wait_post_process()
+            bufs = w.wait_post_process()
+            if bufs is None:
+                continue
+            rk, rv = bufs
             runtime.attn_fwd(q, rk, rv, cm.remote_attn_args_list[st], out_acc, lse_acc, softmax_scale, softcap,
                              max_logits=max_logits)
         max_logits = runtime.reduce_max_logits(max_logits)
@@ -166,7 +249,7 @@ class DistAttnFunc(torch.autograd.Function):
         cm = runtime.calc_meta
         scale, softcap = ctx.softmax_scale, ctx.softcap
         dout = dout.contiguous()
-        works = runtime.fetch_remote_kv(k, v)
+        works = runtime.fetch_remote_kv(k, v, backward=True)
         dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
         dk = torch.zeros(k.shape, dtype=torch.float32, device=k.device)
         dv = torch.zeros(v.shape, dtype=torch.float32, device=v.device)
@@ -174,27 +257,28 @@ class DistAttnFunc(torch.autograd.Function):
         if not cm.local_attn_arg.can_skip or sink is not None:
             # the host stage also produces this rank's partial dsink (rows it owns; reference :663-713)
             runtime.attn_bwd(dout, q, k, v, out, lse, cm.local_attn_arg, dq, dk, dv, scale, softcap, sink=sink, dsink=dsink)
-        reduces: list[WorkWithPostProcessFn] = []
         wire = torch.float32 if runtime.high_precision_reduce else k.dtype
+        runtime.begin_reduce(dk, dv, wire)
+        reduces: list = []
         for st in range(runtime.overlap_degree):
             w = works[st]
-            if w is None:
+            bufs = w.wait_post_process() if w is not None else None
+            if bufs is None:
+                # nothing to compute on; the reduce may still need this rank as an owner (decided from the tables)
+                reduces.append(runtime.reduce_partial_dkv(st, None, None, dk, dv, wire))
                 continue
-            rk, rv = w.wait_post_process()
+            rk, rv = bufs
             arg = cm.remote_attn_args_list[st]
+            dk_p, dv_p = runtime.partial_buffers(st, rk, rv, wire)
             if arg.can_skip:
-                dk_p = torch.zeros(rk.shape, dtype=wire, device=rk.device)
-                dv_p = torch.zeros(rv.shape, dtype=wire, device=rv.device)
+                dk_p.zero_(); dv_p.zero_()
             else:
-                dk_p = torch.empty(rk.shape, dtype=wire, device=rk.device)
-                dv_p = torch.empty(rv.shape, dtype=wire, device=rv.device)
                 a = arg.to_ffa_args(q.device)
                 # fresh (non-accumulating) partial dk/dv in the wire dtype; dq accumulates
                 _lib.ffa_bwd(dout, q, rk, rv, out, lse, dq, dk_p, dv_p, a["q_ranges"], a["k_ranges"], a["attn_type_map"],
                              scale, softcap, accumulate_dkv=False, sm_margin=runtime.sm_margin)
-            reduces.append(runtime.reduce_partial_dkv(st, dk_p, dv_p, dk, dv))
-        for rw in reduces:
-            rw.wait_post_process()
+            reduces.append(runtime.reduce_partial_dkv(st, dk_p, dv_p, dk, dv, wire))
+        runtime.finish_reduce(reduces)
         dsink = runtime.reduce_partial_dsink(dsink)
         if dsink is not None:
             dsink = dsink.to(sink.dtype)

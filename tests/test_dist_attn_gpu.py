@@ -106,12 +106,14 @@ def test_virtual_cp_real_kernels(name):
 
 
 # ---------------------------------------------------------------------------------------------------
-def _cp_worker(rank, world, port, name, with_sink=False):
+def _cp_worker(rank, world, port, name, with_sink=False, engine="nvl", iters=1, degree=None, hp_reduce=False):
     import torch.distributed as dist
     from magiattention_b200.api import calc_attn, compute_pad_size, dispatch, magi_attn_flex_key, undispatch
     from magiattention_b200.common import AttnRanges
 
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["MAGI_B200_KV_EXCHANGE"] = engine
+    os.environ["MAGI_B200_NVL_TIMEOUT_S"] = "20"
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     import datetime
@@ -131,12 +133,26 @@ def _cp_worker(rank, world, port, name, with_sink=False):
             sink = torch.randn(4, H, dtype=torch.float32, device=dev)
             dist.broadcast(sink, 0)
             sink.requires_grad_(True)
+        from magiattention_b200.api import get_runtime_mgr
+        from magiattention_b200.config import DistAttnConfig, OverlapConfig
+        cfg_kw = {}
+        if degree is not None or hp_reduce:
+            cfg_kw["dist_attn_config"] = DistAttnConfig(overlap_config=OverlapConfig(True, degree or 2), high_precision_reduce=hp_reduce)
         key = magi_attn_flex_key(AttnRanges.from_ranges(cfg["q_ranges"]), AttnRanges.from_ranges(cfg["k_ranges"]), cfg["types"],
-                                 T, T, H, HK, D, pad, dist.group.WORLD, chunk_size=chunk)
-        ql, kl, vl = dispatch(q, key), dispatch(k, key), dispatch(v, key)
-        ol, meta = calc_attn(ql, kl, vl, key, sink=sink, return_max_logits=with_sink)
-        out = undispatch(ol, key)
-        out.backward(do)
+                                 T, T, H, HK, D, pad, dist.group.WORLD, chunk_size=chunk, **cfg_kw)
+        if world > 1:
+            assert get_runtime_mgr(key).dist_attn_runtime.engine == engine, "requested exchange engine is not the one running"
+        for it in range(iters):  # several passes: flag epochs advance, both arena slots get reused
+            for x in (q, k, v) + ((sink,) if with_sink else ()):
+                x.grad = None
+            ql, kl, vl = dispatch(q, key), dispatch(k, key), dispatch(v, key)
+            ol, meta = calc_attn(ql, kl, vl, key, sink=sink, return_max_logits=with_sink)
+            out = undispatch(ol, key)
+            out.backward(do)
+        if world > 1 and engine == "nvl":
+            from magiattention_b200.comm.nvl_exchange import NvlDomain
+            torch.cuda.synchronize()
+            NvlDomain.get(dist.group.WORLD).check()
         mask = orc.mask_from_slices(cfg["q_ranges"], cfg["k_ranges"], cfg["types"], T, T)
         qd, kd, vd = q.detach(), k.detach(), v.detach()
         sd = sink.detach() if with_sink else None
@@ -153,15 +169,30 @@ def _cp_worker(rank, world, port, name, with_sink=False):
         for nm, g, r_, l_ in zip(("dq", "dk", "dv"), (q.grad, k.grad, v.grad), ref, lp):
             orc.check_close(nm, g, r_, l_, nm, atol=orc.grad_atol(r_))
     finally:
+        from magiattention_b200.comm.nvl_exchange import NvlDomain
+        NvlDomain.shutdown()
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("engine", ["nvl", "nccl"])
 @pytest.mark.parametrize("name", ["causal", "sliding_window_causal"])
-def test_real_cp_nccl(name):
+def test_real_cp_nccl(name, engine):
+    """Both exchange engines (NVLink peer-memory pulls / NCCL P2P) through the public API against the global oracle."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     world = min(torch.cuda.device_count(), 4)
-    spawn_with_deadline(_cp_worker, world, (name,), deadline_s=300)
+    spawn_with_deadline(_cp_worker, world, (name, False, engine), deadline_s=300)
+
+
+@pytest.mark.parametrize("name,degree,hp", [("varlen_block_causal_2k", 3, False), ("all_types_aspects", 2, True),
+                                            ("sparse_attn_2k", 4, False)])
+def test_real_cp_nvl_multi_pass(name, degree, hp):
+    """NVLink engine over several consecutive forward/backward passes (epoch flags advance, both arena slots are reused),
+    more overlap stages than ranks need, and the fp32 wire dtype of the partial dK/dV."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(torch.cuda.device_count(), 4)
+    spawn_with_deadline(_cp_worker, world, (name, False, "nvl", 4, degree, hp), deadline_s=300)
 
 
 @pytest.mark.parametrize("name", ["uncovered_rows", "all_types_aspects"])

@@ -282,9 +282,9 @@ def test_planner_random_slices_fuzz(seed):
 
 @pytest.mark.parametrize("cp,degree", [(2, 1), (4, 2), (8, 3)])
 def test_pull_plan_equals_group_cast(cp, degree):
-    """comm/peer_exchange.make_pull_plan (the host side of the opt-in peer-memory exchange): pulling the listed row spans
+    """comm/nvl_exchange.make_pull_plan (the host side of the NVLink peer-memory exchange): pulling the listed row spans
     out of the owners' shards reproduces the receive buffer of the naive group_cast for every rank and stage."""
-    from magiattention_b200.comm.peer_exchange import make_pull_plan
+    from magiattention_b200.comm.nvl_exchange import make_pull_plan
 
     for cfg in mask_configs(4):
         sl = _slices(cfg)
@@ -306,7 +306,7 @@ def test_pull_plan_equals_group_cast(cp, degree):
                     out[d0:d0 + n] = kl[s][s0:s0 + n]
                 assert torch.equal(out, want[r])
             # return path: every owner pulls the partial rows of its consumers and adds them == naive group_reduce
-            from magiattention_b200.comm.peer_exchange import make_reduce_pull_plan
+            from magiattention_b200.comm.nvl_exchange import make_reduce_pull_plan
 
             parts = [torch.randn(w.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(r + 7 * st))
                      for r, w in enumerate(want)]
