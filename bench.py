@@ -322,7 +322,7 @@ def main():
         assert pad == 0
         from magiattention_b200.config import DistAttnConfig, OverlapConfig
         degree = int(os.environ.get("B200_OVERLAP_DEGREE", 2 if world <= 2 else 4))
-        cfg = DistAttnConfig(overlap_config=OverlapConfig(enable=True, degree=degree))
+        cfg = DistAttnConfig(overlap_config=OverlapConfig(degree=degree))
         workload["overlap_degree"] = degree
         key = magi_attn_flex_key(AttnRanges.from_ranges(wl["q_ranges"]), AttnRanges.from_ranges(wl["k_ranges"]), wl["types"], S, S,
                                  H, HK, D, pad, dist.group.WORLD, dist_attn_config=cfg, chunk_size=chunk)

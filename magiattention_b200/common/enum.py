@@ -26,3 +26,11 @@ _TO_INT = {v: k for k, v in _FROM_INT.items()}
 class AttnOverlapMode(Enum):
     STATIC = "static"
     DYNAMIC = "dynamic"
+
+
+class AttnRole(Enum):
+    """Which operand of the attention a tensor plays (reference: common/enum.py AttnRole)."""
+
+    QUERY = "query"
+    KEY = "key"
+    VALUE = "value"

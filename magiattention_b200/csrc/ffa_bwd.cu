@@ -27,6 +27,13 @@
 #include "ffa_kernels.h"
 #include "sm100.cuh"
 
+// Timing-only ablation switches for kernel analysis (results become WRONG; never set in the product build):
+//   1 drain skips staging + TMA reduce   2 drain skips its TMEM loads too   4 no dQ MMA   8 exp2 -> fma
+//   16 pass 2 skips the dS^T st.shared   32 lse / delta read once instead of per element group
+#ifndef FFA_BWD_ABL
+#define FFA_BWD_ABL 0
+#endif
+
 namespace ffa {
 using namespace sm100;
 
@@ -238,12 +245,12 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             uint32_t pk[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 l4 = *reinterpret_cast<const float4*>(s_lse + ch * 32 + j * 4);
+              const float4 l4 = *reinterpret_cast<const float4*>(s_lse + ((FFA_BWD_ABL & 32) ? 0 : ch * 32 + j * 4));
               const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int i = j * 4 + e;
-                float x = ex2(fmaf(__uint_as_float(sr[i]), sl2, -lv[e]));
+                float x = (FFA_BWD_ABL & 8) ? fmaf(__uint_as_float(sr[i]), sl2, -lv[e]) : ex2(fmaf(__uint_as_float(sr[i]), sl2, -lv[e]));
                 x = ((bits >> i) & 1u) ? x : 0.f;
                 p[ch * 32 + i] = x;
               }
@@ -267,7 +274,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             uint32_t pk[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 d4 = *reinterpret_cast<const float4*>(s_del + ch * 32 + j * 4);
+              const float4 d4 = *reinterpret_cast<const float4*>(s_del + ((FFA_BWD_ABL & 32) ? 0 : ch * 32 + j * 4));
               const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
               float ds[4];
 #pragma unroll
@@ -277,7 +284,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
             tmem_st16(tDP + ch * 16, pk);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < ((FFA_BWD_ABL & 16) ? 0 : 4); ++j) {
               const int chunk = ch * 4 + j;  // 16-byte chunk (8 q values) inside this thread's 128-byte row
               *reinterpret_cast<uint4*>(sds_row + ((chunk ^ swz) << 4)) =
                   make_uint4(pk[j * 4], pk[j * 4 + 1], pk[j * 4 + 2], pk[j * 4 + 3]);
@@ -372,15 +379,20 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int h2 = 0; h2 < kD / 64; ++h2) {
             uint32_t r[2][32];
-            tmem_ld32(tDQ + h2 * 64, r[0]);
-            tmem_ld32(tDQ + h2 * 64 + 32, r[1]);
-            tc_wait_ld();
+            if (!(FFA_BWD_ABL & 2)) {
+              tmem_ld32(tDQ + h2 * 64, r[0]);
+              tmem_ld32(tDQ + h2 * 64 + 32, r[1]);
+              tc_wait_ld();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[0][i] = r[1][i] = 0;
+            }
             if (h2 == kD / 64 - 1) {
               tc_fence_before();
               mbar_arrive(bar(kBarDrained));  // TMEM dQ region may be overwritten by the next dP
             }
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc, ++chunk_ctr) {
+            for (int cc = 0; cc < ((FFA_BWD_ABL & 1) ? 0 : 2); ++cc, ++chunk_ctr) {
               const int c = h2 * 2 + cc;
               const uint32_t buf = chunk_ctr & 1;
               if (dtid == 0) tma_store_wait_read<1>();  // the reduce that last read this buffer has consumed it
@@ -479,7 +491,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mma_tmemA(tDK, tDP, sQ, it > 0, bar(kBarQEmpty + st));
             if (elect_one()) {
 #pragma unroll
-              for (uint32_t kk = 0; kk < 8; ++kk)
+              for (uint32_t kk = 0; kk < ((FFA_BWD_ABL & 4) ? 0 : 8); ++kk)
                 mma_ss(tDP, smem_desc(mn_hi, sDS + kk * 2048), smem_desc(mn_hi, sK + kk * 2048), id_mm, kk > 0 ? 1u : 0u);
               tc_commit(bar(kBarDQ));
             }

@@ -30,6 +30,12 @@
 #include "ffa_kernels.h"
 #include "sm100.cuh"
 
+// Timing-only ablation switches for kernel analysis (results become WRONG; never set in the product build):
+//   1 exp2 -> fma   2 no block max   4 P not stored to TMEM
+#ifndef FFA_FWD_ABL
+#define FFA_FWD_ABL 0
+#endif
+
 namespace ffa {
 using namespace sm100;
 
@@ -109,6 +115,8 @@ __device__ __forceinline__ float2 softmax_half(const uint32_t* sr, float sl2, fl
       float2 pv;
       if ((i % kEmuPeriod) < kEmuCount) {
         pv = ex2_emu2<kEmuDegree>(x);
+      } else if (FFA_FWD_ABL & 1) {
+        pv = __ffma2_rn(x, make_float2(0.001f, 0.001f), make_float2(1.f, 1.f));
       } else {
         pv.x = ex2(x.x);
         pv.y = ex2(x.y);
@@ -116,7 +124,7 @@ __device__ __forceinline__ float2 softmax_half(const uint32_t* sr, float sl2, fl
       acc4[i & 3] = __fadd2_rn(acc4[i & 3], pv);
       pr[i] = pack2<kBF16>(pv.x, pv.y);
     }
-    tmem_st16(t_dst + c * 16, pr);
+    if (!(FFA_FWD_ABL & 4)) tmem_st16(t_dst + c * 16, pr);
   }
   const float2 a01 = __fadd2_rn(acc4[0], acc4[1]), a23 = __fadd2_rn(acc4[2], acc4[3]);
   return __fadd2_rn(a01, a23);
@@ -234,7 +242,7 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         {
           float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-          for (int i = 0; i < 128; i += 8) {
+          for (int i = 0; i < ((FFA_FWD_ABL & 2) ? 8 : 128); i += 8) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               m4[j] = fmaxf(m4[j], fmaxf(__uint_as_float(sr[i + 2 * j]), __uint_as_float(sr[i + 2 * j + 1])));

@@ -33,37 +33,36 @@ def _gather_global(x_local: torch.Tensor, meta: DispatchMeta, group) -> torch.Te
 
 class _DispatchFunc(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, meta, rank, group, pad):
-        ctx.meta, ctx.rank, ctx.group, ctx.pad = meta, rank, group, pad
-        if pad:
-            x = torch.cat([x, x.new_zeros((pad, *x.shape[1:]))], 0)
+    def forward(ctx, x, meta, rank, group):
+        ctx.meta, ctx.rank, ctx.group = meta, rank, group
         return _take_chunks(x, meta, rank)
 
     @staticmethod
     def backward(ctx, g):
-        full = _gather_global(g.contiguous(), ctx.meta, ctx.group)
-        if ctx.pad:
-            full = full[: full.shape[0] - ctx.pad]
-        return full, None, None, None, None
+        return _gather_global(g.contiguous(), ctx.meta, ctx.group), None, None, None
 
 
 class _UndispatchFunc(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x_local, meta, rank, group, pad):
-        ctx.meta, ctx.rank, ctx.group, ctx.pad = meta, rank, group, pad
-        full = _gather_global(x_local.contiguous(), meta, group)
-        return full[: full.shape[0] - pad] if pad else full
+    def forward(ctx, x_local, meta, rank, group, is_partial_grad):
+        ctx.meta, ctx.rank, ctx.group, ctx.partial = meta, rank, group, is_partial_grad
+        return _gather_global(x_local.contiguous(), meta, group)
 
     @staticmethod
     def backward(ctx, g):
-        if ctx.pad:
-            g = torch.cat([g, g.new_zeros((ctx.pad, *g.shape[1:]))], 0)
+        if ctx.partial and ctx.meta.cp_size > 1:
+            # every rank holds a PARTIAL gradient of the global tensor: sum over ranks before taking the local chunks
+            # (reference: undispatch_func(is_partial_grad=True) reduce-scatters, functional/dispatch.py:96-136)
+            g = g.contiguous().clone()
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
         return _take_chunks(g, ctx.meta, ctx.rank), None, None, None, None
 
 
-def dispatch_func(x, meta: DispatchMeta, rank: int, group, pad_size: int = 0) -> torch.Tensor:
-    return _DispatchFunc.apply(x, meta, rank, group, pad_size)
+def dispatch_func(x_global: torch.Tensor, meta: DispatchMeta, rank: int, group) -> torch.Tensor:
+    """Global [total_seqlen (padded), ...] -> this rank's permuted shard."""
+    return _DispatchFunc.apply(x_global, meta, rank, group)
 
 
-def undispatch_func(x_local, meta: DispatchMeta, rank: int, group, pad_size: int = 0) -> torch.Tensor:
-    return _UndispatchFunc.apply(x_local, meta, rank, group, pad_size)
+def undispatch_func(x_local: torch.Tensor, meta: DispatchMeta, rank: int, group, is_partial_grad: bool = False) -> torch.Tensor:
+    """This rank's shard -> global [total_seqlen (padded), ...] (all-gather + unpermute)."""
+    return _UndispatchFunc.apply(x_local, meta, rank, group, is_partial_grad)

@@ -68,12 +68,19 @@ class DistAttnRuntime:
         group_reduce as grouped ncclSend/ncclRecv, comm/group_collective.py."""
 
     def __init__(self, comm_meta: CommMeta, calc_meta: CalcMeta, cp_group: dist.ProcessGroup | None,
-                 sm_margin: int = 0, high_precision_reduce: bool = False, all_comm_metas: list[CommMeta] | None = None):
+                 sm_margin: int = 0, high_precision_reduce: bool = False, all_comm_metas: list[CommMeta] | None = None,
+                 deterministic: bool = False):
         self.comm_meta = comm_meta
         self.calc_meta = calc_meta
         self.cp_group = cp_group
         self.overlap_degree = calc_meta.overlap_degree
-        self.sm_margin = sm_margin
+        if sm_margin != 0:
+            raise NotImplementedError("sm_margin: the B200 exchange runs on copy engines and needs no SM reservation; the "
+                                      "attention kernels are one-CTA-per-tile grids and cannot leave SMs idle")
+        if deterministic:
+            from .flex_flash_attn import _reject_deterministic
+            _reject_deterministic()
+        self.sm_margin = 0
         self.high_precision_reduce = high_precision_reduce
         self.cp_size = 1 if cp_group is None else dist.get_world_size(cp_group)
         # communication volume bookkeeping (rows of K == rows of V) for exposed-comm accounting

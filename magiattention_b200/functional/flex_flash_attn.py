@@ -7,13 +7,17 @@ behaviour for ``flex_flash_attn_func`` (:1066-1455), ``_flex_flash_attn_forward`
 ``libb200_ffa.so`` (include/b200_ffa.h) — hand-written sm_100a kernels; there is no Triton,
 no library GEMM and no CPU fallback.
 
-Differences that are deliberate:
-  * the kernels reduce overlapping q rows in registers/TMEM, so ``disable_fwd_atomic_reduction``,
-    ``disable_bwd_dkv_atomic_reduction``, ``deterministic`` (always deterministic except the fp32 dQ
-    reduction order), ``ref_block_size``, ``max_seqlen_q``, ``swap_ab``, ``pack_gqa``, ``cat_gqa``,
-    ``swap_bwd_qk_loop``, ``auto_range_merge`` are accepted and have no effect on results;
-  * unsupported knobs raise like the reference's FA4 guard does (:1399-1421): ``softcap``,
-    ``sparse_load``, ``index_attn`` / ``index_attn_indices``, sink layout ``"shd"``.
+Differences that are deliberate — a knob either works, is a pure scheduling hint of the reference's
+Hopper kernel with no meaning here, or raises:
+  * scheduling hints (results never depend on them in the reference either): ``disable_fwd_atomic_reduction`` /
+    ``disable_bwd_dkv_atomic_reduction`` (promises that q / k ranges do not overlap — the kernels here never use global
+    atomics for out / dk / dv), ``ref_block_size``, ``max_seqlen_q``, ``swap_ab``, ``pack_gqa``, ``cat_gqa``,
+    ``swap_bwd_qk_loop``, ``auto_range_merge`` (tile shapes / loop orders / a range pre-merge of the sm90 kernel; this
+    backend builds its own tile->slice plan) are accepted;
+  * unsupported knobs raise like the reference's FA4 guard does (:1399-1421): ``softcap``, ``sparse_load``,
+    ``index_attn`` / ``index_attn_indices``, sink layout ``"shd"``, ``deterministic=True`` (out / lse / dk / dv are
+    bitwise reproducible, the fp32 dQ reduction order across kv tiles is not), ``sm_margin != 0`` (one-CTA-per-tile
+    grids cannot leave SMs idle; the CP exchange here runs on copy engines and needs none).
 Attention ``sink`` (fp32, layouts ``"sh"`` / ``"ssh"``, at most 8 sink tokens like the reference kernel) and
 ``return_max_logits`` are supported.
 """
@@ -25,6 +29,20 @@ from .. import _lib
 from ..common.forward_meta import AttnForwardMeta
 
 __all__ = ["flex_flash_attn_func", "ffa_fa4_func", "_flex_flash_attn_forward", "_flex_flash_attn_backward", "FlexFlashAttnFunc"]
+
+
+DETERMINISTIC_SUPPORTED = False
+
+
+def _reject_deterministic() -> None:
+    raise NotImplementedError("deterministic=True: out, lse, dk and dv of the B200 kernels are bitwise reproducible, but dq is "
+                              "reduced across kv tiles with TMA reduce-adds whose order is not fixed")
+
+
+def _reject_sm_margin(sm_margin: int) -> None:
+    if sm_margin:
+        raise NotImplementedError("sm_margin != 0 is not supported: the B200 kernels are one-CTA-per-tile grids that cannot "
+                                  "leave SMs idle (the CP exchange runs on copy engines and needs no SM reservation)")
 
 
 def _maybe_contiguous(x: torch.Tensor | None) -> torch.Tensor | None:
@@ -65,6 +83,9 @@ def _flex_flash_attn_forward(
     tests/test_attn/test_flex_flash_attn.py:362-540)."""
     if unused.get("sparse_load") or unused.get("index_attn"):
         raise RuntimeError("B200 FFA backend does not support sparse_load / index_attn")
+    if deterministic:
+        _reject_deterministic()
+    _reject_sm_margin(sm_margin)
     return_max_logits = bool(unused.get("return_max_logits", False))
     max_logits = unused.get("max_logits")
     if return_max_logits and max_logits is None:
@@ -114,6 +135,9 @@ def _flex_flash_attn_backward(
     disjoint key sets add exactly.  A given fp32 ``dq`` is accumulated into; given fp32 ``dk``/``dv`` are
     accumulated into as well (reference: flex_flash_attn.py:637-647, dist_attn.py:1432).  With a ``sink`` the
     fp32 ``dsink`` (zero-initialised when not given, :652-657) is accumulated into and returned."""
+    if deterministic:
+        _reject_deterministic()
+    _reject_sm_margin(sm_margin)
     dout, q, k, v, sink, out, q_ranges, k_ranges = (
         _maybe_contiguous(x) for x in (dout, q, k, v, sink, out, q_ranges, k_ranges))
     if sink is not None and dsink is None:
@@ -206,7 +230,7 @@ def flex_flash_attn_func(
     )
     bad = [name for name, on in {
         "index_attn_indices": index_attn_indices is not None, "softcap": softcap != 0.0,
-        "sparse_load": sparse_load, "index_attn": index_attn,
+        "sparse_load": sparse_load, "index_attn": index_attn, "deterministic": deterministic, "sm_margin": sm_margin != 0,
     }.items() if on]
     assert not bad, f"B200 FFA backend does not support the following features: {bad}."
     assert k_ranges is not None, "k_ranges must be provided together with q_ranges"

@@ -56,25 +56,32 @@ def _roll_impl(x_local: torch.Tensor, shift: int, meta: DispatchMeta, rank: int,
     out = torch.empty_like(x)
     plans = roll_spans(meta, shift)
     ops, pending = [], []
-    # receives in my destination order, sends in every destination's order: both sides enumerate the same plan, so the
-    # k-th message between a pair of ranks is the same span on both ends
+    # both sides enumerate the same plan, so the k-th message between a pair of ranks is the same span on both ends
+    recvs: dict[int, list] = {}
+    sends: dict[int, list] = {}
     for (src, s0, d0, n) in plans[rank]:
         if src == rank:
             out[d0:d0 + n].copy_(x[s0:s0 + n])
-        elif batched:
-            ops.append(dist.P2POp(dist.irecv, out[d0:d0 + n], _global_rank(group, src), group))
         else:
-            pending.append(dist.irecv(out[d0:d0 + n], _global_rank(group, src), group=group))
+            recvs.setdefault(src, []).append(out[d0:d0 + n])
     for dst_rank, spans in enumerate(plans):
-        if dst_rank == rank:
+        if dst_rank != rank:
+            for (src, s0, _, n) in spans:
+                if src == rank:
+                    sends.setdefault(dst_rank, []).append(x[s0:s0 + n])
+    for peer in sorted(set(recvs) | set(sends)):
+        gp = _global_rank(group, peer)
+        if batched:
+            ops += [dist.P2POp(dist.irecv, t, gp, group) for t in recvs.get(peer, [])]
+            ops += [dist.P2POp(dist.isend, t, gp, group) for t in sends.get(peer, [])]
             continue
-        for (src, s0, _, n) in spans:
-            if src != rank:
-                continue
-            if batched:
-                ops.append(dist.P2POp(dist.isend, x[s0:s0 + n], _global_rank(group, dst_rank), group))
-            else:
-                pending.append(dist.isend(x[s0:s0 + n], _global_rank(group, dst_rank), group=group))
+        # un-batched NCCL P2P ops of one rank run in issue order on one stream: two ranks that both post their receive
+        # first wait for each other forever.  Matched pair order (reference functional/roll.py:285-350): the lower rank
+        # sends first, the higher rank receives first; peers are visited in increasing order on every rank.
+        first, second = (sends, recvs) if rank < peer else (recvs, sends)
+        for table in (first, second):
+            fn = dist.isend if table is sends else dist.irecv
+            pending += [fn(t, gp, group=group) for t in table.get(peer, [])]
     if ops:
         pending = dist.batch_isend_irecv(ops)
     for w in pending:

@@ -137,7 +137,7 @@ def _cp_worker(rank, world, port, name, with_sink=False, engine="nvl", iters=1, 
         from magiattention_b200.config import DistAttnConfig, OverlapConfig
         cfg_kw = {}
         if degree is not None or hp_reduce:
-            cfg_kw["dist_attn_config"] = DistAttnConfig(overlap_config=OverlapConfig(True, degree or 2), high_precision_reduce=hp_reduce)
+            cfg_kw["dist_attn_config"] = DistAttnConfig(overlap_config=OverlapConfig(degree=degree or 2), high_precision_reduce=hp_reduce)
         key = magi_attn_flex_key(AttnRanges.from_ranges(cfg["q_ranges"]), AttnRanges.from_ranges(cfg["k_ranges"]), cfg["types"],
                                  T, T, H, HK, D, pad, dist.group.WORLD, chunk_size=chunk, **cfg_kw)
         if world > 1:

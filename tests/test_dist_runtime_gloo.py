@@ -55,6 +55,7 @@ def _install_fake_kernels():
 def _runtime_body(rank, world, name, degree, alg=None, hp_reduce=False):
     from magiattention_b200.api import calc_attn, compute_pad_size, dispatch, magi_attn_flex_key, undispatch
     from magiattention_b200.common import AttnRanges
+    from magiattention_b200.common.enum import AttnOverlapMode
     from magiattention_b200.config import DispatchConfig, DistAttnConfig, OverlapConfig
 
     _install_fake_kernels()
@@ -70,7 +71,9 @@ def _runtime_body(rank, world, name, degree, alg=None, hp_reduce=False):
                              H, HK, D, pad, dist.group.WORLD,
                              dist_attn_config=DistAttnConfig(
                                  dispatch_config=DispatchConfig(alg=alg) if alg is not None else DispatchConfig(),
-                                 overlap_config=OverlapConfig(True, degree), high_precision_reduce=hp_reduce), chunk_size=chunk)
+                                 overlap_config=(OverlapConfig(degree=degree) if degree is not None else
+                                                 OverlapConfig(mode=AttnOverlapMode.DYNAMIC, degree=None)),
+                                 high_precision_reduce=hp_reduce), chunk_size=chunk)
     ol, meta = calc_attn(dispatch(q, key), dispatch(k, key), dispatch(v, key), key)
     out = undispatch(ol, key)
     out.backward(do)
@@ -113,7 +116,7 @@ def _sink_body(rank, world, name, degree):
         x.requires_grad_(True)
     key = magi_attn_flex_key(AttnRanges.from_ranges(cfg["q_ranges"]), AttnRanges.from_ranges(cfg["k_ranges"]), cfg["types"], T, T,
                              H, HK, D, pad, dist.group.WORLD,
-                             dist_attn_config=DistAttnConfig(overlap_config=OverlapConfig(True, degree)), chunk_size=chunk)
+                             dist_attn_config=DistAttnConfig(overlap_config=OverlapConfig(degree=degree)), chunk_size=chunk)
     ol, meta = calc_attn(dispatch(q, key), dispatch(k, key), dispatch(v, key), key, sink=sink, return_max_logits=True)
     out = undispatch(ol, key)
     out.backward(do)
@@ -154,7 +157,7 @@ def _new_mask_body(rank, world, degree):
         dist.broadcast(x, 0)
     key0 = magi_attn_flex_key(AttnRanges.from_ranges(base["q_ranges"]), AttnRanges.from_ranges(base["k_ranges"]), base["types"],
                               T, T, H, HK, D, pad, dist.group.WORLD,
-                              dist_attn_config=DistAttnConfig(overlap_config=OverlapConfig(True, degree)), chunk_size=chunk)
+                              dist_attn_config=DistAttnConfig(overlap_config=OverlapConfig(degree=degree)), chunk_size=chunk)
     ql, kl, vl = (dispatch(x, key0).requires_grad_(True) for x in (q, k, v))
     for name in ("sliding_window_causal", "sparse_attn_2k"):
         cfg = cfgs[name]
@@ -201,7 +204,7 @@ def _roll_body(rank, world):
     key = magi_attn_flex_key(AttnRanges.from_ranges([[0, T]]), AttnRanges.from_ranges([[0, T]]), "causal", T, T, 2, 2, 8, pad,
                              dist.group.WORLD, chunk_size=chunk)
     mgr = get_runtime_mgr(key)
-    Tp = T + pad
+    Tp, chunk = key.total_seqlen_q, key.chunk_size  # padded total / the chunk size the key settled on (capped like the reference)
     torch.manual_seed(3)
     g = torch.randn(Tp, 3, dtype=torch.float64)  # the padded global tensor as the dispatch sees it
     dist.broadcast(g, 0)

@@ -235,23 +235,36 @@ def test_dispatch_algorithms_partition_and_plan(alg, cp):
 
 
 def test_config_classes_match_reference_surface():
-    """Config objects as the reference's docs construct them (api/magi_attn_interface.py:1385-1395) are accepted and hashable."""
+    """Config objects as the reference's docs construct them (api/magi_attn_interface.py:1385-1395) are accepted and hashable;
+    every knob either works or raises."""
     from magiattention_b200.common.enum import AttnOverlapMode
-    from magiattention_b200.config import (DispatchConfig, DistAttnConfig, GrpCollConfig, MinHeapDispatchAlg, OverlapConfig,
-                                           SequentialDispatchAlg, SortedSequentialSelectAlg, ToppHeapDispatchAlg, UniformOverlapAlg)
+    from magiattention_b200.config import (BSDispatchAlg, DispatchConfig, DistAttnConfig, DPDispatchAlg, GreedyOverlapAlg,
+                                           GrpCollConfig, LBDispatchAlg, MinHeapDispatchAlg, OverlapConfig, SequentialDispatchAlg,
+                                           SortedSequentialSelectAlg, ToppHeapDispatchAlg, UniformOverlapAlg)
 
     c = DistAttnConfig(dispatch_config=DispatchConfig(chunk_size=512, alg=MinHeapDispatchAlg()),
-                       overlap_config=OverlapConfig(enable=True, mode=AttnOverlapMode.STATIC, degree=2, min_chunk_size=512,
+                       overlap_config=OverlapConfig(mode=AttnOverlapMode.STATIC, degree=2, min_chunk_size=512,
                                                     max_num_chunks=64, alg=UniformOverlapAlg()),
                        grpcoll_config=GrpCollConfig())
     assert hash(c) == hash(DistAttnConfig(dispatch_config=DispatchConfig(chunk_size=512, alg=MinHeapDispatchAlg()),
-                                          overlap_config=OverlapConfig(True, 2)))
+                                          overlap_config=OverlapConfig(AttnOverlapMode.STATIC, 2)))
     assert c.dispatch_config.planner_alg == "min_heap" and c.overlap_config.num_stages(8) == 2
     assert DispatchConfig(alg=SequentialDispatchAlg()).planner_alg == "sequential"
     assert DispatchConfig(alg=SortedSequentialSelectAlg()).planner_alg == "sorted_sequential"
-    assert DispatchConfig(alg=ToppHeapDispatchAlg(top_p=0.5)).planner_alg == "min_heap"
-    assert OverlapConfig(degree=0).num_stages(8) == 1 and OverlapConfig(degree=None).num_stages(8) == 4
-    assert OverlapConfig(degree=None).num_stages(2) == 2 and OverlapConfig(degree=3).num_stages(1) == 1
+    for alg in (ToppHeapDispatchAlg(top_p=0.5), LBDispatchAlg(), DPDispatchAlg(), BSDispatchAlg()):
+        with pytest.raises(NotImplementedError):
+            DispatchConfig(alg=alg)
+    with pytest.raises(NotImplementedError):
+        OverlapConfig(degree=2, alg=GreedyOverlapAlg())
+    # reference semantics of degree (overlap_solver.py:72-147): default 1, 0 = no overlap, None needs the dynamic mode
+    assert OverlapConfig().degree == 1 and not OverlapConfig().enable and OverlapConfig(degree=2).enable
+    z = OverlapConfig(degree=0)
+    assert z.no_overlap and z.degree == 1 and z.max_num_chunks == 1 and z.num_stages(8) == 1
+    dyn = OverlapConfig(mode=AttnOverlapMode.DYNAMIC, degree=None)
+    assert dyn.num_stages(8) == 4 and dyn.num_stages(2) == 2 and OverlapConfig(degree=3).num_stages(1) == 1
+    assert OverlapConfig(mode=AttnOverlapMode.DYNAMIC, degree=None, dynamic_max_degree=2).num_stages(8) == 2
+    with pytest.raises(AssertionError):
+        OverlapConfig(degree=None)  # static mode needs an explicit degree
     with pytest.raises(NotImplementedError):
         DispatchConfig(uneven_shard=True)
 

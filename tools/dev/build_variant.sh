@@ -5,7 +5,7 @@ name=$1; shift
 cd "$(dirname "$0")/../.."
 out=magiattention_b200/lib/variants; mkdir -p $out/$name
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -diag-suppress 177"
-for f in ffa_api ffa_plan ffa_fwd ffa_fwd64 ffa_fwd2 ffa_bwd ffa_aux; do
+for f in ffa_api ffa_plan ffa_fwd ffa_bwd ffa_aux nvl_exchange; do
   nvcc $FLAGS "$@" -c magiattention_b200/csrc/$f.cu -o $out/$name/$f.o &
 done
 wait
