@@ -95,10 +95,13 @@ def run(workload: dict, steps: int, warmup: int, rank: int, world: int, local_ra
         ffa_fa4_func(q, k, v, q_ranges=qrt, k_ranges=krt, attn_type_map=tyt, reuse_attn_arg=False)
         torch.cuda.synchronize()
 
+        fwd_only = bool(workload.get("fwd_only"))
+
         def step():
             q.grad = k.grad = v.grad = None
             o, _ = ffa_fa4_func(q, k, v, q_ranges=qrt, k_ranges=krt, attn_type_map=tyt, reuse_attn_arg=True)
-            o.backward(do)
+            if not fwd_only:
+                o.backward(do)
         api = "ffa_fa4_func(reuse_attn_arg=True)"
     else:
         from magi_attention.api import calc_attn, compute_pad_size, dispatch, magi_attn_flex_key
@@ -114,7 +117,7 @@ def run(workload: dict, steps: int, warmup: int, rank: int, world: int, local_ra
             attn_mask_type=[AttnMaskType(names[t]) for t in ty], total_seqlen_q=S, total_seqlen_k=S,
             num_heads_q=HQ, num_heads_kv=HK, head_dim=D, pad_size=pad, chunk_size=chunk, cp_group_or_mesh=dist.group.WORLD,
             dist_attn_config=DistAttnConfig(dispatch_config=DispatchConfig(alg=MinHeapDispatchAlg()),
-                                            overlap_config=OverlapConfig(enable=True, degree=2)))
+                                            overlap_config=OverlapConfig(degree=2)))
         S_loc = (S + pad) // world
         # local shards drawn directly (i.i.d. data: statistically what dispatch() of a global tensor hands this rank)
         gl = torch.Generator(device="cpu").manual_seed(42 + 10 * rank)
@@ -122,14 +125,31 @@ def run(workload: dict, steps: int, warmup: int, rank: int, world: int, local_ra
                        for h in (HQ, HK, HK, HQ))
         q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)
 
+        fwd_only = bool(workload.get("fwd_only"))
+
         def step():
             q.grad = k.grad = v.grad = None
             o, _ = calc_attn(q, k, v, key)
-            o.backward(do)
+            if not fwd_only:
+                o.backward(do)
         api = "magi_attn_flex_key / calc_attn (backend fa4, chunk 2048, degree 2, MinHeap)"
     for _ in range(max(warmup, 1)):
         step()
     torch.cuda.synchronize()
     setup_s = time.time() - t_setup
     ms = timed(step, steps)
+    if os.environ.get("BENCH_REF_SPLIT") == "1" and world == 1 and not fwd_only:
+        # developer aid: the reference's forward-only and backward-only times (its own kernel benchmark times them apart)
+        def f_only():
+            with torch.no_grad():
+                ffa_fa4_func(q, k, v, q_ranges=qrt, k_ranges=krt, attn_type_map=tyt, reuse_attn_arg=True)
+        ms_f = timed(f_only, steps)
+        o, _ = ffa_fa4_func(q, k, v, q_ranges=qrt, k_ranges=krt, attn_type_map=tyt, reuse_attn_arg=True)
+
+        def b_only():
+            q.grad = k.grad = v.grad = None
+            o.backward(do, retain_graph=True)
+        b_only()
+        ms_b = timed(b_only, steps)
+        print(f"REF_SPLIT fwd {ms_f:.3f} ms  bwd {ms_b:.3f} ms  fwd+bwd {ms:.3f} ms", file=sys.stderr)
     return {"ms_per_step": ms, "api": api, "setup_s": setup_s}

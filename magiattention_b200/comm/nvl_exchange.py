@@ -373,7 +373,7 @@ class NvlKVExchange:
         """Call on the compute stream right after the stage-``st`` backward kernel: tell the owners their rows are ready."""
         c, dom = self._cur, self.dom
         owners = self.owners[st]
-        self._signal(("pr", st), lambda: [dom.flag_addr(o, _W_PART_READY + self.rank * _MAX_STAGES + st) for o in owners],
+        self._signal(("pr_out", st), lambda: [dom.flag_addr(o, _W_PART_READY + self.rank * _MAX_STAGES + st) for o in owners],
                      c["p"], torch.cuda.current_stream(dom.device))
 
     def begin_reduce(self, dk: torch.Tensor, dv: torch.Tensor, wire_dtype: torch.dtype) -> None:
@@ -396,7 +396,7 @@ class NvlKVExchange:
             sv = torch.empty((n, hk, d), dtype=wire_dtype, device=dom.device)
             keep += [sk, sv]
             cons = self.part_sources[st]
-            self._wait(("pr", st), lambda: [dom.flag_addr(self.rank, _W_PART_READY + s * _MAX_STAGES + st) for s in cons],
+            self._wait(("pr_in", st), lambda: [dom.flag_addr(self.rank, _W_PART_READY + s * _MAX_STAGES + st) for s in cons],
                        c["p"], rs)
             spans, dst_spans, src_spans, pos = [], [], [], 0
             for (cr, s0, d0, nr) in plan:
