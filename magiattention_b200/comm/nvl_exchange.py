@@ -376,14 +376,24 @@ class NvlKVExchange:
         self._signal(("pr_out", st), lambda: [dom.flag_addr(o, _W_PART_READY + self.rank * _MAX_STAGES + st) for o in owners],
                      c["p"], torch.cuda.current_stream(dom.device))
 
+    def mark_local_done(self) -> None:
+        """Call right after the local (host-stage) backward has been enqueued: the folds must not start before it."""
+        self._cur["local_done"] = torch.cuda.current_stream(self.dom.device).record_event()
+
     def begin_reduce(self, dk: torch.Tensor, dv: torch.Tensor, wire_dtype: torch.dtype) -> None:
-        """Owner side of the dKV return path, enqueued once per backward on the reduce stream after the local backward:
-        for every stage wait for the consumers' partials, pull them (copy engines) and fold them into dk / dv."""
+        """Owner side of the dKV return path: for every stage wait for the consumers' partials, pull them (copy engines)
+        and fold them into dk / dv, all on the reduce stream, ordered only behind the local backward.
+
+        HOST ORDER MATTERS: call this AFTER every ``partial_ready`` of the pass has been enqueued.  A wait enqueued before
+        this rank's own signals can deadlock two ranks against each other through implicit host/device synchronisation
+        (a cudaMalloc in the caching allocator orders later launches behind the pending wait kernel: each rank then holds
+        back the signal the other one waits for).  With every signal already in the streams, a pending wait only ever
+        depends on work the peers enqueue on their own."""
         from .. import _lib
 
         c, dom = self._cur, self.dom
         rs = dom.reduce_stream
-        rs.wait_stream(torch.cuda.current_stream(dom.device))
+        rs.wait_event(c["local_done"])
         prb = c["part_row_bytes"]
         hk, d = c["hk"], c["d"]
         keep = []
@@ -392,8 +402,9 @@ class NvlKVExchange:
             if not plan:
                 continue
             n = sum(x[3] for x in plan)
-            sk = torch.empty((n, hk, d), dtype=wire_dtype, device=dom.device)
-            sv = torch.empty((n, hk, d), dtype=wire_dtype, device=dom.device)
+            with torch.cuda.stream(rs):  # staging lives in the reduce stream's allocator pool: written and read only there
+                sk = torch.empty((n, hk, d), dtype=wire_dtype, device=dom.device)
+                sv = torch.empty((n, hk, d), dtype=wire_dtype, device=dom.device)
             keep += [sk, sv]
             cons = self.part_sources[st]
             self._wait(("pr_in", st), lambda: [dom.flag_addr(self.rank, _W_PART_READY + s * _MAX_STAGES + st) for s in cons],

@@ -124,9 +124,14 @@ class DistAttnRuntime:
             works.append(w)
         return works
 
+    def mark_local_backward_done(self) -> None:
+        if self._stub is None and self.nvl is not None:
+            self.nvl.mark_local_done()
+
     def begin_reduce(self, dk: torch.Tensor, dv: torch.Tensor, wire: torch.dtype) -> None:
-        """Owner side of the dKV return path (nvl engine): enqueue, once per backward and after the local backward, the
-        pulls + folds of every stage on the reduce stream.  The NCCL engine reduces stage by stage instead."""
+        """Owner side of the dKV return path (nvl engine): the pulls + folds of every stage on the reduce stream, ordered
+        behind the local backward only.  Enqueued AFTER the stage loop (every partial-ready signal of this rank is in its
+        stream by then — see NvlKVExchange.begin_reduce).  The NCCL engine reduces stage by stage instead."""
         if self._stub is None and self.nvl is not None:
             self.nvl.begin_reduce(dk, dv, wire)
 
@@ -265,7 +270,7 @@ class DistAttnFunc(torch.autograd.Function):
             # the host stage also produces this rank's partial dsink (rows it owns; reference :663-713)
             runtime.attn_bwd(dout, q, k, v, out, lse, cm.local_attn_arg, dq, dk, dv, scale, softcap, sink=sink, dsink=dsink)
         wire = torch.float32 if runtime.high_precision_reduce else k.dtype
-        runtime.begin_reduce(dk, dv, wire)
+        runtime.mark_local_backward_done()
         reduces: list = []
         for st in range(runtime.overlap_degree):
             w = works[st]
@@ -285,6 +290,7 @@ class DistAttnFunc(torch.autograd.Function):
                 _lib.ffa_bwd(dout, q, rk, rv, out, lse, dq, dk_p, dv_p, a["q_ranges"], a["k_ranges"], a["attn_type_map"],
                              scale, softcap, accumulate_dkv=False, sm_margin=runtime.sm_margin)
             reduces.append(runtime.reduce_partial_dkv(st, dk_p, dv_p, dk, dv, wire))
+        runtime.begin_reduce(dk, dv, wire)
         runtime.finish_reduce(reduces)
         dsink = runtime.reduce_partial_dsink(dsink)
         if dsink is not None:
