@@ -4,7 +4,7 @@ N=${1:-2}; STEPS=${2:-5}
 mkdir -p gpurun_out; cd "$(dirname "$0")/../.."
 nvidia-smi -L; nvidia-smi topo -m 2>/dev/null | head -12
 timeout 1200 python -m pytest tests/test_dist_attn_gpu.py -m gpu -q -x 2>&1 | tail -15 | tee gpurun_out/cp_tests_n$N.log
-for eng in nvl nccl; do
+for eng in ${ENGINES:-nvl nccl}; do
   MAGI_B200_KV_EXCHANGE=$eng timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
     bench.py --gpus $N --steps $STEPS --warmup 3 > gpurun_out/bench_n${N}_$eng.json 2> gpurun_out/bench_n${N}_$eng.err
   python - <<P
