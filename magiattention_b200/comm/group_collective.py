@@ -55,7 +55,7 @@ def group_cast(
     output_split_sizes: Sequence[int],
     dst_indices: Sequence[Sequence[int]],
     src_index: Sequence[int],
-    group: dist.ProcessGroup | None = None,
+    group: dist.ProcessGroup | None,
     async_op: bool = False,
     cast_lse: bool = False,
     input_lse: torch.Tensor | None = None,
@@ -150,7 +150,7 @@ def group_reduce(
     output_split_sizes: Sequence[int],
     dst_index: Sequence[int],
     src_indices: Sequence[Sequence[int]],
-    group: dist.ProcessGroup | None = None,
+    group: dist.ProcessGroup | None,
     async_op: bool = False,
     reduce_op: str = "sum",
     acc_reduce: bool = True,

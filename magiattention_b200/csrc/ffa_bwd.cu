@@ -30,8 +30,27 @@
 // Timing-only ablation switches for kernel analysis (results become WRONG; never set in the product build):
 //   1 drain skips staging + TMA reduce   2 drain skips its TMEM loads too   4 no dQ MMA   8 exp2 -> fma
 //   16 pass 2 skips the dS^T st.shared   32 lse / delta read once instead of per element group
+//   64 drain stages into smem but issues no TMA reduce   128 drain issues the TMA reduce without writing the staging
 #ifndef FFA_BWD_ABL
 #define FFA_BWD_ABL 0
+#endif
+// (measured and rejected, round 2: draining dQ straight from registers with sector-coalesced red.global.add.v2.f32 —
+//  tcgen05.ld.16x256b fragments, four lanes per 32-byte sector, no shared-memory staging — is 29 % SLOWER than the
+//  smem-staged TMA reduce-add: SM-issued reductions are far more expensive at L2 than UTMAREDG; tools/probe/probe_ld.cu
+//  keeps the fragment-layout probe.)
+
+// Developer timeline (-DFFA_TRACE): CTA 0 stamps %clock64 at the hand-off points of iterations [32, 96) — see ffa_fwd.cu.
+#ifdef FFA_TRACE
+__device__ unsigned long long g_trace_bwd[4][64][8];
+#define FFA_TRB(role, it, ev)                                                                                        \
+  do {                                                                                                                \
+    if (blockIdx.x == 0 && (it) >= 32u && (it) < 96u && (threadIdx.x & 31) == 0) g_trace_bwd[role][(it) - 32u][ev] = clock64(); \
+  } while (0)
+extern "C" __attribute__((visibility("default"))) int b200_debug_trace_bwd(unsigned long long* dst) {
+  return cudaMemcpyFromSymbol(dst, g_trace_bwd, sizeof(g_trace_bwd)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define FFA_TRB(role, it, ev) do {} while (0)
 #endif
 
 namespace ffa {
@@ -225,8 +244,10 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mbar_wait(bar(kBarQFull + st), (it >> 1) & 1);  // LSE2 / Delta of this block are in smem
           const float* s_lse = reinterpret_cast<const float*>(smem + kSmemLse + st * 512) + half * 64;
           const float* s_del = reinterpret_cast<const float*>(smem + kSmemDelta + st * 512) + half * 64;
+          if (wid == 0) FFA_TRB(1, it, 0);
           mbar_wait(bar(kBarS), it & 1);
           tc_fence_after();
+          if (wid == 0) FFA_TRB(1, it, 1);
           float p[64];
           // ---- pass 1: P^T = exp2(S^T * sl2 - lse2[q]) -> TMEM (A operand of the dV MMA)
 #pragma unroll
@@ -262,10 +283,13 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(bar(kBarP));
+          if (wid == 0) FFA_TRB(1, it, 2);
           // ---- pass 2: dS^T = P^T o (dP^T - delta[q]) -> TMEM (A of dK MMA) and smem (A of dQ MMA)
           mbar_wait(bar(kBarDP), it & 1);
           tc_fence_after();
+          if (wid == 0) FFA_TRB(1, it, 3);
           if (it > 0) mbar_wait(bar(kBarDQ), (it - 1) & 1);  // previous dQ MMA has finished reading sdS
+          if (wid == 0) FFA_TRB(1, it, 4);
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {
             uint32_t dr[32];
@@ -294,6 +318,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tc_fence_before();
           fence_proxy_async_smem();
           mbar_arrive(bar(kBarDS));
+          if (wid == 0) FFA_TRB(1, it, 5);
         }
       }
     }
@@ -372,8 +397,10 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (!gm.init(sl, C0)) continue;
         for (int b = 0; b < gm.nblk; ++b, ++it) {
           const int rs = gm.r_start + b * kBlockM;
+          if (wid == 8) FFA_TRB(2, it, 0);
           mbar_wait(bar(kBarDQ), it & 1);
           tc_fence_after();
+          if (wid == 8) FFA_TRB(2, it, 1);
           // two halves of 64 columns: the TMEM region is released (kBarDrained) as soon as the second half sits
           // in registers, i.e. after staging only the first half
 #pragma unroll
@@ -390,6 +417,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (h2 == kD / 64 - 1) {
               tc_fence_before();
               mbar_arrive(bar(kBarDrained));  // TMEM dQ region may be overwritten by the next dP
+              if (wid == 8) FFA_TRB(2, it, 2);
             }
 #pragma unroll
             for (int cc = 0; cc < ((FFA_BWD_ABL & 1) ? 0 : 2); ++cc, ++chunk_ctr) {
@@ -399,19 +427,20 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               named_bar_sync(1, 128);
               uint8_t* dst = stage_row + buf * kDQChunkBytes;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < ((FFA_BWD_ABL & 128) ? 0 : 8); ++j) {
                 *reinterpret_cast<float4*>(dst + ((j ^ swz) << 4)) = make_float4(
                     __uint_as_float(r[cc][4 * j]) * args.scale, __uint_as_float(r[cc][4 * j + 1]) * args.scale,
                     __uint_as_float(r[cc][4 * j + 2]) * args.scale, __uint_as_float(r[cc][4 * j + 3]) * args.scale);
               }
               fence_proxy_async_smem();
               named_bar_sync(1, 128);
-              if (dtid == 0) {
+              if (dtid == 0 && !(FFA_BWD_ABL & 64)) {
                 tma_reduce_add_3d(&tmDQ, smem_base + kSmemDQ + buf * kDQChunkBytes, c * 32, hq, rs);
                 tma_store_commit();
               }
             }
           }
+          if (wid == 8) FFA_TRB(2, it, 3);
         }
       }
     }
@@ -476,8 +505,10 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const uint32_t sQ = smem_base + kSmemQ + st * kTileBytes, sDO = smem_base + kSmemDO;
             const bool has_next = it + 1 < n_it;
             // dV += P^T dO
+            FFA_TRB(0, it, 0);
             mbar_wait(bar(kBarP), it & 1);
             tc_fence_after();
+            FFA_TRB(0, it, 1);
             mma_tmemA(tDV, tS, sDO, it > 0, bar(kBarDOEmpty));  // dO_it no longer needed once dV retires
             // S_{it+1} (S region is free after dV in tensor-pipe order)
             if (has_next) {
@@ -486,8 +517,10 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               mma_kmajor(tS, sK, smem_base + kSmemQ + nst * kTileBytes, bar(kBarS));
             }
             // dK += dS^T Q ; dQ = dS K
+            FFA_TRB(0, it, 2);
             mbar_wait(bar(kBarDS), it & 1);
             tc_fence_after();
+            FFA_TRB(0, it, 3);
             mma_tmemA(tDK, tDP, sQ, it > 0, bar(kBarQEmpty + st));
             if (elect_one()) {
 #pragma unroll
@@ -498,9 +531,12 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             __syncwarp();
             // dP_{it+1} once the dQ tile has been drained out of the shared TMEM region
             if (has_next) {
+              FFA_TRB(0, it, 4);
               mbar_wait(bar(kBarDrained), it & 1);
+              FFA_TRB(0, it, 5);
               mbar_wait(bar(kBarDOFull), (it + 1) & 1);
               tc_fence_after();
+              FFA_TRB(0, it, 6);
               mma_kmajor(tDP, sV, smem_base + kSmemDO, bar(kBarDP));
             }
           }
@@ -538,7 +574,9 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int b = 0; b < gm.nblk; ++b, ++it) {
               const int rs = gm.r_start + b * kBlockM;
               const uint32_t st = it & 1, ph = (it >> 1) & 1;
+              FFA_TRB(3, it, 0);
               mbar_wait(bar(kBarQEmpty + st), ph ^ 1);
+              FFA_TRB(3, it, 1);
               if (elect_one()) {
                 mbar_arrive_expect_tx(bar(kBarQFull + st), kTileBytes + 1024);
                 const uint32_t sQ = smem_base + kSmemQ + st * kTileBytes;
@@ -550,6 +588,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               }
               __syncwarp();
               mbar_wait(bar(kBarDOEmpty), (it & 1) ^ 1);
+              FFA_TRB(3, it, 2);
               if (elect_one()) {
                 mbar_arrive_expect_tx(bar(kBarDOFull), kTileBytes);
                 const uint32_t sDO = smem_base + kSmemDO;

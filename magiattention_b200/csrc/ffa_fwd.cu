@@ -31,9 +31,25 @@
 #include "sm100.cuh"
 
 // Timing-only ablation switches for kernel analysis (results become WRONG; never set in the product build):
-//   1 exp2 -> fma   2 no block max   4 P not stored to TMEM
+//   1 exp2 -> fma   2 no block max   4 P not stored to TMEM   8 S not loaded from TMEM   16 K/V ring filled only once
+//   32 no PV MMAs   64 no S MMAs
 #ifndef FFA_FWD_ABL
 #define FFA_FWD_ABL 0
+#endif
+
+// Developer timeline (-DFFA_TRACE): CTA 0 stamps %clock64 at the hand-off points of iterations [64, 128) into a device
+// array that b200_debug_trace_fwd() copies out (tools/dev/trace_fwd.py prints it).  Compiled out of the product build.
+#ifdef FFA_TRACE
+__device__ unsigned long long g_trace_fwd[4][64][8];
+#define FFA_TR(role, it, ev)                                                                                         \
+  do {                                                                                                                \
+    if (blockIdx.x == 0 && (it) >= 64u && (it) < 128u && (threadIdx.x & 31) == 0) g_trace_fwd[role][(it) - 64u][ev] = clock64(); \
+  } while (0)
+extern "C" __attribute__((visibility("default"))) int b200_debug_trace_fwd(unsigned long long* dst) {
+  return cudaMemcpyFromSymbol(dst, g_trace_fwd, sizeof(g_trace_fwd)) == cudaSuccess ? 0 : -1;
+}
+#else
+#define FFA_TR(role, it, ev) do {} while (0)
 #endif
 
 namespace ffa {
@@ -216,12 +232,20 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int b = 0; b < g.nblk; ++b) {
         const int bs = g.c_min + b * kBlockN;
         if (!tg.active(bs)) continue;
+        if ((wid & 3) == 0) FFA_TR(1 + t, n_act, 0);
         mbar_wait(bar(kBarS + t), n_act & 1);
         tc_fence_after();
+        if ((wid & 3) == 0) FFA_TR(1 + t, n_act, 1);
         uint32_t sr[128];
+        if (FFA_FWD_ABL & 8) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[c * 32]));
-        tc_wait_ld();
+          for (int c = 0; c < 128; ++c) sr[c] = 0x3f800000u + c + n_act;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[c * 32]));
+          tc_wait_ld();
+        }
+        if ((wid & 3) == 0) FFA_TR(1 + t, n_act, 2);
         if (!tg.full(bs)) {
           const int lo_rel = lo_r - bs, hi_rel = hi_r - bs;
 #pragma unroll
@@ -280,11 +304,13 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(bar(kBarP + t));  // P[:, 0:64) (and any O rescale) visible: first 4 PV k-steps may start
+        if ((wid & 3) == 0) FFA_TR(1 + t, n_act, 3);
         const float2 acc_hi = softmax_half<kBF16>(&sr[64], sl2, mneg, tS + 32);
         l_sum += (acc_lo.x + acc_lo.y) + (acc_hi.x + acc_hi.y);
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(bar(kBarPhi + t));
+        if ((wid & 3) == 0) FFA_TR(1 + t, n_act, 4);
         ++n_act;
       }
     }
@@ -420,22 +446,25 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t buf = li % kStages;
         const uint32_t sV = sKV + buf * kTileBytes;
         const uint32_t tP = tmem + kTmemS + t * 128, tOt = tmem + kTmemO + t * 128;
+        FFA_TR(0, n_act_t - 1, 4 * t + 0);
         mbar_wait(bar(kBarFull + buf), (li / kStages) & 1);
         mbar_wait(bar(kBarP + t), (n_act_t - 1) & 1);  // first 64 columns of P_t are in TMEM
         tc_fence_after();
+        FFA_TR(0, n_act_t - 1, 4 * t + 1);
         if (elect_one()) {
 #pragma unroll
-          for (uint32_t kk = 0; kk < 4; ++kk)
+          for (uint32_t kk = 0; kk < ((FFA_FWD_ABL & 32) ? 0 : 4); ++kk)
             mma_ts(tOt, tP + kk * 8, smem_desc(desc_v_hi, sV + kk * 2048), idesc_pv, (n_act_t > 1 || kk > 0) ? 1u : 0u);
         }
         __syncwarp();
         mbar_wait(bar(kBarPhi + t), (n_act_t - 1) & 1);  // second half
         tc_fence_after();
+        FFA_TR(0, n_act_t - 1, 4 * t + 2);
         pend -= 1u << (4 * buf);
         const bool release = ((pend >> (4 * buf)) & 15u) == 0;
         if (elect_one()) {
 #pragma unroll
-          for (uint32_t kk = 4; kk < 8; ++kk)
+          for (uint32_t kk = 4; kk < ((FFA_FWD_ABL & 32) ? 0 : 8); ++kk)
             mma_ts(tOt, tP + kk * 8, smem_desc(desc_v_hi, sV + kk * 2048), idesc_pv, 1u);
           if (release) tc_commit(bar(kBarEmpty + buf));
         }
@@ -445,7 +474,7 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t tSt = tmem + kTmemS + t * 128;
         if (elect_one()) {
 #pragma unroll
-          for (uint32_t kk = 0; kk < kD / 16; ++kk) {  // contraction over the head dim
+          for (uint32_t kk = 0; kk < ((FFA_FWD_ABL & 64) ? 0 : kD / 16); ++kk) {  // contraction over the head dim
             const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
             mma_ss(tSt, smem_desc(DESC_KMAJOR, sQ + t * kTileBytes + off), smem_desc(DESC_KMAJOR, sK + off), idesc_s,
                    kk > 0 ? 1u : 0u);
@@ -453,6 +482,7 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tc_commit(bar(kBarS + t));
         }
         __syncwarp();
+        FFA_TR(0, (t == 0 ? n_act0 : n_act1), 4 * t + 3);  // S of block n_act (0-based) issued
       };
 
       SliceCursor cur;
@@ -523,13 +553,19 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int which = 0; which < 2; ++which) {
             const uint32_t li = 2 * blk + which, buf = li % kStages;
+            FFA_TR(3, uint32_t(blk), 2 * which);
             mbar_wait(bar(kBarEmpty + buf), ((li / kStages) & 1) ^ 1);
+            FFA_TR(3, uint32_t(blk), 2 * which + 1);
             if (elect_one()) {
-              mbar_arrive_expect_tx(bar(kBarFull + buf), kTileBytes);
-              const CUtensorMap* tm = which == 0 ? &tmK : &tmV;
+              if ((FFA_FWD_ABL & 16) && li >= uint32_t(kStages)) {
+                mbar_arrive(bar(kBarFull + buf));
+              } else {
+                mbar_arrive_expect_tx(bar(kBarFull + buf), kTileBytes);
+                const CUtensorMap* tm = which == 0 ? &tmK : &tmV;
 #pragma unroll
-              for (uint32_t bx = 0; bx < kBoxes; ++bx)
-                tma_load_3d(sKV + buf * kTileBytes + bx * kBoxBytes, tm, bar(kBarFull + buf), 64 * bx, hk, bs);
+                for (uint32_t bx = 0; bx < kBoxes; ++bx)
+                  tma_load_3d(sKV + buf * kTileBytes + bx * kBoxBytes, tm, bar(kBarFull + buf), 64 * bx, hk, bs);
+              }
             }
             __syncwarp();
           }
