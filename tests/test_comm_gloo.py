@@ -58,7 +58,7 @@ def _cast_reduce_body(rank, world, T, chunk, degree, slices):
                   src_index=[a.src_index_list for a in args], output_split_sizes=[a.output_split_size_list for a in args])
         want_k = orc.group_cast_ref(kl, **kw)[rank]
         want_v = orc.group_cast_ref(vl, **kw)[rank]
-        work = group_cast((kl[rank], vl[rank]), None, async_op=True, **args[rank].to_group_cast_args())
+        work = group_cast((kl[rank], vl[rank]), None, group=dist.group.WORLD, async_op=True, **args[rank].to_group_cast_args())
         rk, rv = work.wait_post_process()
         assert torch.equal(rk, want_k) and torch.equal(rv, want_v)
         # received rows really are the global rows the plan says (zero-redundant fetch of visible keys only)
@@ -71,7 +71,7 @@ def _cast_reduce_body(rank, world, T, chunk, degree, slices):
                                     dst_index=[a["dst_index"] for a in rkw], src_indices=[a["src_indices"] for a in rkw],
                                     output_split_sizes=[a["output_split_sizes"] for a in rkw])[rank]
         out = base[rank].clone()
-        w = group_reduce(parts[rank], out, async_op=True, **rkw[rank])
+        w = group_reduce(parts[rank], out, group=dist.group.WORLD, async_op=True, **rkw[rank])
         w.wait_post_process()
         torch.testing.assert_close(out, want, atol=1e-6, rtol=1e-6)
         with pytest.raises(RuntimeError):
