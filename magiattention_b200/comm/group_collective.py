@@ -66,15 +66,23 @@ def group_cast(
     row-split identically; ``output`` mirrors it (allocated when ``None``).  Returns a work whose
     ``wait_post_process(output)`` yields the filled output after ordering the current stream behind the
     transfer."""
-    if cast_lse:
-        raise NotImplementedError("cast_lse (q/o communication) is outside the B200 hot path")
     ins = _as_tuple(input)
+    lse_out = None
+    if cast_lse:
+        # the lse rows [rows, heads] travel with the same splits as one more member of the tuple
+        # (reference: cast_lse, grpcoll/_group_collective.py:81-205)
+        assert input_lse is not None, "cast_lse=True needs input_lse"
+        assert not isinstance(input, (tuple, list)), "cast_lse takes a single input tensor"
+        ins = (ins[0], input_lse)
+        if output is not None:
+            assert output_lse is not None, "cast_lse=True with a given output needs output_lse"
+            output = (output, output_lse)
     assert len(input_split_sizes) == len(dst_indices)
     assert len(output_split_sizes) == len(src_index)
     n_out = int(sum(output_split_sizes))
     if output is None:
         outs = tuple(t.new_empty((n_out, *t.shape[1:])) for t in ins)
-        output = outs if isinstance(input, (tuple, list)) else outs[0]
+        output = outs if (isinstance(input, (tuple, list)) or cast_lse) else outs[0]
     else:
         outs = _as_tuple(output)
     for t in ins:
@@ -143,6 +151,24 @@ def _range_add(dst: torch.Tensor, src: torch.Tensor, dst_spans: list[tuple[int, 
             dst[d0:d1] += src[s0:s1].to(dst.dtype)
 
 
+def _lse_merge_rows(out: torch.Tensor, lse: torch.Tensor, out2: torch.Tensor, lse2: torch.Tensor) -> None:
+    """(out, lse) <- LSE-merge with (out2, lse2), in place on contiguous row spans (correct_attn_out_lse semantics)."""
+    if out.shape[0] == 0:
+        return
+    if out.is_cuda:
+        from .. import _lib
+
+        _lib.lse_merge(out, lse, out2.contiguous(), lse2.contiguous())
+        return
+    if os.environ.get("MAGI_B200_ALLOW_HOST_COMM_TEST", "0") != "1":
+        raise RuntimeError("group_reduce on host tensors is test-only (set MAGI_B200_ALLOW_HOST_COMM_TEST=1)")
+    l = torch.logaddexp(lse, lse2)
+    w1 = torch.exp(lse - l).nan_to_num(0.0).unsqueeze(-1)
+    w2 = torch.exp(lse2 - l).nan_to_num(0.0).unsqueeze(-1)
+    out.copy_((w1 * out.float() + w2 * out2.float()).to(out.dtype))
+    lse.copy_(l)
+
+
 def group_reduce(
     input: _TensorOrTuple,
     output: _TensorOrTuple,
@@ -160,24 +186,33 @@ def group_reduce(
     **kwargs,
 ) -> WorkWithPostProcessFn:
     """Transpose of group_cast with accumulation: input split i goes to rank ``dst_index[i]``; output split
-    j (+)= the splits received from every rank of ``src_indices[j]``.  ``acc_reduce=False`` zeroes the
-    output first.  Only ``reduce_op="sum"`` is on the hot path (dK/dV)."""
-    if reduce_op != "sum":
-        raise NotImplementedError(f"reduce_op={reduce_op!r} (q/o communication) is outside the B200 hot path")
+    j (+)= the splits received from every rank of ``src_indices[j]``.  ``acc_reduce=False`` zeroes the output first.
+    ``reduce_op``: "sum" (the dK/dV hot path), "avg" (mean; an accumulated old value counts as one contribution) or "lse"
+    (log-sum-exp weighted merge of partial attention outputs with ``input_lse`` / ``output_lse`` fp32 [rows, heads] —
+    the reduction of the reference's q/o communication, common/range_op/_range_reduce.py:239-357)."""
+    if reduce_op not in ("sum", "avg", "lse"):
+        raise ValueError(f"Invalid reduce_op {reduce_op!r}: expected 'sum', 'avg' or 'lse'")
     ins = _as_tuple(input)
     outs = _as_tuple(output)
     assert len(ins) == len(outs)
+    if reduce_op == "lse":
+        # log-sum-exp weighted merge of partial attention outputs (q/o communication): the lse rows travel as a second tensor
+        assert len(ins) == 1 and input_lse is not None and output_lse is not None, "reduce_op='lse' needs input_lse / output_lse"
+        assert input_lse.dtype == torch.float32 and output_lse.dtype == torch.float32, "lse tensors must be fp32"
     assert len(input_split_sizes) == len(dst_index)
     assert len(output_split_sizes) == len(src_indices)
     if comm_dtype is not None:
         ins = tuple(t.to(comm_dtype) for t in ins)
+    send = ins + ((input_lse,) if reduce_op == "lse" else ())
     rank = dist.get_rank(group)
     if not acc_reduce:
         for t in outs:
             t.zero_()
+        if reduce_op == "lse":
+            output_lse.fill_(float("-inf"))
 
     n_recv = int(sum(sz * len(srcs) for sz, srcs in zip(output_split_sizes, src_indices)))
-    stages = tuple(t.new_empty((n_recv, *t.shape[1:])) for t in ins)
+    stages = tuple(t.new_empty((n_recv, *t.shape[1:])) for t in send)
     ops: list[dist.P2POp] = []
     self_queue: list[tuple[int, int]] = []
     off = 0
@@ -187,12 +222,13 @@ def group_reduce(
                 self_queue.append((off, sz))
             else:
                 peer = _global_rank(group, d)
-                for t in ins:
+                for t in send:
                     ops.append(dist.P2POp(dist.isend, t[off : off + sz], peer, group))
         off += sz
     dst_spans: list[tuple[int, int]] = []
     src_spans: list[tuple[int, int]] = []
     self_adds: list[tuple[int, int, int]] = []
+    counts: list[tuple[int, int, int]] = []  # (out offset, rows, number of contributions) per output split
     off = 0
     spos = 0
     self_pos = 0
@@ -211,15 +247,30 @@ def group_reduce(
                     dst_spans.append((off, off + sz))
                     src_spans.append((spos, spos + sz))
                     spos += sz
+            counts.append((off, sz, len(srcs)))
         off += sz
     works = _launch(ops, async_op)
     cache_key = (tuple(output_split_sizes), tuple(tuple(s) for s in src_indices), rank)
 
     def post(*a, **k):
+        if reduce_op == "lse":
+            t_out, t_in, st, st_lse = outs[0], ins[0], stages[0], stages[1]
+            for (o, so, sz) in self_adds:
+                _lse_merge_rows(t_out[o : o + sz], output_lse[o : o + sz], t_in[so : so + sz], input_lse[so : so + sz])
+            for (d0, d1), (s0, s1) in zip(dst_spans, src_spans):
+                _lse_merge_rows(t_out[d0:d1], output_lse[d0:d1], st[s0:s1], st_lse[s0:s1])
+            return a[0] if a else output
         for t_out, t_in, st in zip(outs, ins, stages):
             for (o, so, sz) in self_adds:
                 t_out[o : o + sz] += t_in[so : so + sz].to(t_out.dtype)
             _range_add(t_out, st, dst_spans, src_spans, cache_key)
+            if reduce_op == "avg":
+                # reference range_avg_reduce_kernel (common/range_op/_range_reduce.py:152-231): the accumulated old value
+                # counts as one contribution; without accumulation the mean is over the received splits only
+                for (o, sz, n) in counts:
+                    div = n + 1 if acc_reduce else n
+                    if div > 1:
+                        t_out[o : o + sz].div_(div)
         return a[0] if a else output
 
     return WorkWithPostProcessFn(GeneralWork(works), post, async_op=async_op)

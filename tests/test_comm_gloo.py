@@ -78,6 +78,79 @@ def _cast_reduce_body(rank, world, T, chunk, degree, slices):
             w.wait_post_process()  # one-shot semantics (reference comm/work.py:83-114)
 
 
+def _reduce_ops_body(rank, world, T, chunk, degree, slices):
+    """reduce_op 'avg' / 'lse' and cast_lse against a naive world-level restatement
+    (reference semantics: common/range_op/_range_reduce.py:152-357, grpcoll/_group_collective.py:81-408)."""
+    from magiattention_b200.comm import group_cast, group_reduce
+
+    dm, comm, calc = _plan(T, world, chunk, degree, slices)
+    H, Dh = 2, 4
+    for st in range(degree):
+        args = [comm[r].kv_group_collective_args_list[st] for r in range(world)]
+        gen = lambda seed, *shape: torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+        # ---- cast_lse: (x, lse) rows travel together
+        xs = [gen(10 + r, dm.shard_seqlen, H, Dh) for r in range(world)]
+        ls = [gen(20 + r, dm.shard_seqlen, H) for r in range(world)]
+        kw = dict(input_split_sizes=[a.input_split_size_list for a in args], dst_indices=[a.dst_indices_list for a in args],
+                  src_index=[a.src_index_list for a in args], output_split_sizes=[a.output_split_size_list for a in args])
+        want_x, want_l = orc.group_cast_ref(xs, **kw)[rank], orc.group_cast_ref(ls, **kw)[rank]
+        gx, gl = group_cast(xs[rank], None, group=dist.group.WORLD, cast_lse=True, input_lse=ls[rank],
+                            **args[rank].to_group_cast_args()).wait_post_process()
+        assert torch.equal(gx, want_x) and torch.equal(gl, want_l)
+        # ---- the transposed reduce with every op
+        rkw = [a.to_group_reduce_args() for a in args]
+        parts = [gen(100 + r, sum(a.output_split_size_list), H, Dh) for r, a in enumerate(args)]
+        plse = [gen(300 + r, sum(a.output_split_size_list), H) for r, a in enumerate(args)]
+        base = [gen(200 + r, dm.shard_seqlen, H, Dh) for r in range(world)]
+        blse = [gen(400 + r, dm.shard_seqlen, H) for r in range(world)]
+        # naive: walk every sender's input splits, deliver to the owner's output split in table order
+        my = rkw[rank]
+        contrib = [[] for _ in my["output_split_sizes"]]  # per output split: list of (rows, lse rows)
+        for s in range(world):
+            off, k_of = 0, {}
+            for sz, d in zip(rkw[s]["input_split_sizes"], rkw[s]["dst_index"]):
+                if sz > 0 and d == rank:
+                    # the j-th split s sends to me lands in my j-th output split that lists s
+                    j = k_of.get("n", 0)
+                    outs_with_s = [i for i, (osz, srcs) in enumerate(zip(my["output_split_sizes"], my["src_indices"])) if osz > 0 and s in srcs]
+                    contrib[outs_with_s[j]].append((parts[s][off:off + sz], plse[s][off:off + sz]))
+                    k_of["n"] = j + 1
+                off += sz
+        for acc in (True, False):
+            want_avg, want_o, want_l = base[rank].clone(), base[rank].clone(), blse[rank].clone()
+            if not acc:
+                want_avg.zero_(); want_o.zero_(); want_l.fill_(float("-inf"))
+            o = 0
+            for (sz, cs) in zip(my["output_split_sizes"], contrib):
+                if sz > 0:
+                    tot = want_avg[o:o + sz] + sum(c[0] for c in cs) if cs else want_avg[o:o + sz]
+                    div = (len(cs) + 1) if acc else max(len(cs), 1)
+                    want_avg[o:o + sz] = tot / div if (len(cs) + (1 if acc else 0)) > 1 else tot
+                    for (x2, l2) in cs:
+                        l1 = want_l[o:o + sz]
+                        l = torch.logaddexp(l1, l2)
+                        w1, w2 = torch.exp(l1 - l).nan_to_num(0.0), torch.exp(l2 - l).nan_to_num(0.0)
+                        want_o[o:o + sz] = w1.unsqueeze(-1) * want_o[o:o + sz] + w2.unsqueeze(-1) * x2
+                        want_l[o:o + sz] = l
+                o += sz
+            out = base[rank].clone()
+            group_reduce(parts[rank], out, group=dist.group.WORLD, reduce_op="avg", acc_reduce=acc, **my).wait_post_process()
+            torch.testing.assert_close(out, want_avg, atol=1e-5, rtol=1e-5)
+            out, ol = base[rank].clone(), blse[rank].clone()
+            group_reduce(parts[rank], out, group=dist.group.WORLD, reduce_op="lse", acc_reduce=acc, input_lse=plse[rank],
+                         output_lse=ol, **my).wait_post_process()
+            torch.testing.assert_close(out, want_o, atol=1e-5, rtol=1e-5)
+            torch.testing.assert_close(ol, want_l, atol=1e-5, rtol=1e-5)
+    with pytest.raises(ValueError):
+        group_reduce(parts[rank], out, group=dist.group.WORLD, reduce_op="max", **my)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_group_reduce_avg_lse_and_cast_lse_gloo(world):
+    T = 512
+    _run(world, _reduce_ops_body, T, 16, 2, [(0, T, 0, T, 1), ])
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_group_cast_reduce_gloo(world):
     T = 512
