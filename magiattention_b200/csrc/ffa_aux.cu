@@ -50,7 +50,41 @@ __global__ void lse_merge_kernel(TO* __restrict__ out, float* __restrict__ lse, 
 // Row-span accumulate.  Several entries may target the SAME dst span (an output split of group_reduce that
 // receives partial dK/dV from several ranks); such entries must be ADJACENT in the lists: the first entry of a
 // run owns the span and folds every source of the run in one pass (fp32 accumulate, no read-modify-write race).
-template <typename TD, typename TS>
+template <typename T> struct Vec4;  // four consecutive elements moved with one load / store
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<__half> { using type = uint2; };
+template <> struct Vec4<__nv_bfloat16> { using type = uint2; };
+template <typename T> __device__ __forceinline__ void load4(const T* p, float (&x)[4]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&x)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+}
+template <> __device__ __forceinline__ void load4<__half>(const __half* p, float (&x)[4]) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  const __half2 a = *reinterpret_cast<const __half2*>(&v.x), b = *reinterpret_cast<const __half2*>(&v.y);
+  x[0] = __low2float(a); x[1] = __high2float(a); x[2] = __low2float(b); x[3] = __high2float(b);
+}
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&x)[4]) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  x[0] = __uint_as_float(v.x << 16); x[1] = __uint_as_float(v.x & 0xffff0000u);
+  x[2] = __uint_as_float(v.y << 16); x[3] = __uint_as_float(v.y & 0xffff0000u);
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, const float (&x)[4]);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float (&x)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+}
+template <> __device__ __forceinline__ void store4<__half>(__half* p, const float (&x)[4]) {
+  const __half2 a = __floats2half2_rn(x[0], x[1]), b = __floats2half2_rn(x[2], x[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&x)[4]) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]), b = __floats2bfloat162_rn(x[2], x[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+
+// kVec: four elements per thread with 8 / 16 byte accesses (row_elems % 4 == 0 and 16-byte aligned bases, checked by the
+// launcher); otherwise the scalar form.  HBM-bound: one read of every source span, one read-modify-write of the dst span.
+template <typename TD, typename TS, bool kVec>
 __global__ void range_reduce_kernel(TD* __restrict__ dst, const TS* __restrict__ src, const int2* __restrict__ dr,
                                     const int2* __restrict__ sr, int n, int64_t row_elems) {
   const int r = blockIdx.y;
@@ -68,10 +102,23 @@ __global__ void range_reduce_kernel(TD* __restrict__ dst, const TS* __restrict__
   }
   const int64_t len = int64_t(d.y - d.x) * row_elems;
   TD* dp = dst + int64_t(d.x) * row_elems;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += int64_t(gridDim.x) * blockDim.x) {
-    float acc = to_f(dp[i]);
-    for (int k = 0; k < run; ++k) acc += to_f(src[int64_t(sr[r + k].x) * row_elems + i]);
-    dp[i] = from_f<TD>(acc);
+  if constexpr (kVec) {
+    for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < len; i += int64_t(gridDim.x) * blockDim.x * 4) {
+      float acc[4], x[4];
+      load4<TD>(dp + i, acc);
+      for (int k = 0; k < run; ++k) {
+        load4<TS>(src + int64_t(sr[r + k].x) * row_elems + i, x);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] += x[e];
+      }
+      store4<TD>(dp + i, acc);
+    }
+  } else {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < len; i += int64_t(gridDim.x) * blockDim.x) {
+      float acc = to_f(dp[i]);
+      for (int k = 0; k < run; ++k) acc += to_f(src[int64_t(sr[r + k].x) * row_elems + i]);
+      dp[i] = from_f<TD>(acc);
+    }
   }
 }
 
@@ -249,9 +296,15 @@ int b200_range_reduce_sum(void* dst, int32_t dst_dtype, const void* src, int32_t
     using TD = decltype(ta);
     using TS = decltype(tb);
     dim3 grid(64, num_ranges);
-    range_reduce_kernel<TD, TS><<<grid, 256, 0, stream>>>(static_cast<TD*>(dst), static_cast<const TS*>(src),
-                                                         reinterpret_cast<const int2*>(dst_ranges),
-                                                         reinterpret_cast<const int2*>(src_ranges), num_ranges, row_elems);
+    const bool vec = (row_elems % 4 == 0) && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) % 16 == 0);
+    if (vec)
+      range_reduce_kernel<TD, TS, true><<<grid, 256, 0, stream>>>(static_cast<TD*>(dst), static_cast<const TS*>(src),
+                                                                 reinterpret_cast<const int2*>(dst_ranges),
+                                                                 reinterpret_cast<const int2*>(src_ranges), num_ranges, row_elems);
+    else
+      range_reduce_kernel<TD, TS, false><<<grid, 256, 0, stream>>>(static_cast<TD*>(dst), static_cast<const TS*>(src),
+                                                                  reinterpret_cast<const int2*>(dst_ranges),
+                                                                  reinterpret_cast<const int2*>(src_ranges), num_ranges, row_elems);
     return cudaGetLastError() == cudaSuccess ? int(B200_OK) : int(B200_ERR_CUDA);
   });
 }

@@ -34,6 +34,19 @@
 #ifndef FFA_BWD_ABL
 #define FFA_BWD_ABL 0
 #endif
+// Register budget per role (threads x regs must fit 64K: 256 x COMPUTE + 128 x DRAIN + 128 x OTHER).  The dQ drain warps hold
+// a whole 128 x 128 fp32 tile in registers so that the shared TMEM region is handed back to the MMA warp right after the
+// loads instead of after the first two staged chunks (the measured hold time of the region fell from ~990 to ~250 clocks).
+#ifndef FFA_BWD_REGS_COMPUTE
+#define FFA_BWD_REGS_COMPUTE 136
+#endif
+#ifndef FFA_BWD_REGS_DRAIN
+#define FFA_BWD_REGS_DRAIN 168
+#endif
+#ifndef FFA_BWD_REGS_OTHER
+#define FFA_BWD_REGS_OTHER 72
+#endif
+static_assert(256 * FFA_BWD_REGS_COMPUTE + 128 * FFA_BWD_REGS_DRAIN + 128 * FFA_BWD_REGS_OTHER <= 65536, "register budget");
 // (measured and rejected, round 2: draining dQ straight from registers with sector-coalesced red.global.add.v2.f32 —
 //  tcgen05.ld.16x256b fragments, four lanes per 32-byte sector, no shared-memory staging — is 29 % SLOWER than the
 //  smem-staged TMA reduce-add: SM-issued reductions are far more expensive at L2 than UTMAREDG; tools/probe/probe_ld.cu
@@ -215,7 +228,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   if (wid < 8) {
     // ================================ compute warpgroups ================================
-    setmaxnreg_inc<152>();
+    setmaxnreg_inc<FFA_BWD_REGS_COMPUTE>();
     const int half = wid >> 2;                       // which 64 q columns of the block
     const int krow = (wid & 3) * 32 + lane;          // kv row inside the tile == TMEM lane
     const int c = C0 + krow;                         // global kv index
@@ -379,7 +392,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // dQ tile (128 q rows x 128 d, fp32) : TMEM -> registers (x scale) -> 128B-swizzled smem chunk of 32 columns
     // -> cp.reduce.async.bulk.tensor (TMA reduce-add into the fp32 global dq).  The TMA engine does the L2
     // reductions in full lines; the SM only pays 8 st.shared.v4 per thread per chunk.
-    setmaxnreg_dec<96>();
+    setmaxnreg_inc<FFA_BWD_REGS_DRAIN>();
     const uint32_t lane_off = uint32_t((wid & 3) * 32) << 16;
     const uint32_t tDQ = tmem + lane_off + kTmemDP;
     const int qrow_in_blk = (wid & 3) * 32 + lane;
@@ -401,43 +414,38 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mbar_wait(bar(kBarDQ), it & 1);
           tc_fence_after();
           if (wid == 8) FFA_TRB(2, it, 1);
-          // two halves of 64 columns: the TMEM region is released (kBarDrained) as soon as the second half sits
-          // in registers, i.e. after staging only the first half
+          // the whole tile goes to registers first, so the TMEM region is released (kBarDrained) before any staging
+          uint32_t r[kD / 32][32];
+          if (!(FFA_BWD_ABL & 2)) {
 #pragma unroll
-          for (int h2 = 0; h2 < kD / 64; ++h2) {
-            uint32_t r[2][32];
-            if (!(FFA_BWD_ABL & 2)) {
-              tmem_ld32(tDQ + h2 * 64, r[0]);
-              tmem_ld32(tDQ + h2 * 64 + 32, r[1]);
-              tc_wait_ld();
-            } else {
+            for (int c = 0; c < kD / 32; ++c) tmem_ld32(tDQ + c * 32, r[c]);
+            tc_wait_ld();
+          } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) r[0][i] = r[1][i] = 0;
+            for (int c = 0; c < kD / 32; ++c)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[c][i] = 0;
+          }
+          tc_fence_before();
+          mbar_arrive(bar(kBarDrained));  // TMEM dQ region may be overwritten by the next dP
+          if (wid == 8) FFA_TRB(2, it, 2);
+#pragma unroll
+          for (int c = 0; c < ((FFA_BWD_ABL & 1) ? 0 : kD / 32); ++c, ++chunk_ctr) {
+            const uint32_t buf = chunk_ctr & 1;
+            if (dtid == 0) tma_store_wait_read<1>();  // the reduce that last read this buffer has consumed it
+            named_bar_sync(1, 128);
+            uint8_t* dst = stage_row + buf * kDQChunkBytes;
+#pragma unroll
+            for (int j = 0; j < ((FFA_BWD_ABL & 128) ? 0 : 8); ++j) {
+              *reinterpret_cast<float4*>(dst + ((j ^ swz) << 4)) = make_float4(
+                  __uint_as_float(r[c][4 * j]) * args.scale, __uint_as_float(r[c][4 * j + 1]) * args.scale,
+                  __uint_as_float(r[c][4 * j + 2]) * args.scale, __uint_as_float(r[c][4 * j + 3]) * args.scale);
             }
-            if (h2 == kD / 64 - 1) {
-              tc_fence_before();
-              mbar_arrive(bar(kBarDrained));  // TMEM dQ region may be overwritten by the next dP
-              if (wid == 8) FFA_TRB(2, it, 2);
-            }
-#pragma unroll
-            for (int cc = 0; cc < ((FFA_BWD_ABL & 1) ? 0 : 2); ++cc, ++chunk_ctr) {
-              const int c = h2 * 2 + cc;
-              const uint32_t buf = chunk_ctr & 1;
-              if (dtid == 0) tma_store_wait_read<1>();  // the reduce that last read this buffer has consumed it
-              named_bar_sync(1, 128);
-              uint8_t* dst = stage_row + buf * kDQChunkBytes;
-#pragma unroll
-              for (int j = 0; j < ((FFA_BWD_ABL & 128) ? 0 : 8); ++j) {
-                *reinterpret_cast<float4*>(dst + ((j ^ swz) << 4)) = make_float4(
-                    __uint_as_float(r[cc][4 * j]) * args.scale, __uint_as_float(r[cc][4 * j + 1]) * args.scale,
-                    __uint_as_float(r[cc][4 * j + 2]) * args.scale, __uint_as_float(r[cc][4 * j + 3]) * args.scale);
-              }
-              fence_proxy_async_smem();
-              named_bar_sync(1, 128);
-              if (dtid == 0 && !(FFA_BWD_ABL & 64)) {
-                tma_reduce_add_3d(&tmDQ, smem_base + kSmemDQ + buf * kDQChunkBytes, c * 32, hq, rs);
-                tma_store_commit();
-              }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (dtid == 0 && !(FFA_BWD_ABL & 64)) {
+              tma_reduce_add_3d(&tmDQ, smem_base + kSmemDQ + buf * kDQChunkBytes, c * 32, hq, rs);
+              tma_store_commit();
             }
           }
           if (wid == 8) FFA_TRB(2, it, 3);
@@ -446,7 +454,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     if (dtid == 0) tma_store_wait<0>();
   } else {
-    setmaxnreg_dec<96>();
+    setmaxnreg_dec<FFA_BWD_REGS_OTHER>();
     if (wid == 12) {
       {
         // ================================ MMA issuer ================================
