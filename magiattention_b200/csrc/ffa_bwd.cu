@@ -46,6 +46,12 @@
 #ifndef FFA_BWD_REGS_OTHER
 #define FFA_BWD_REGS_OTHER 72
 #endif
+// dK operand source: 1 = dS^T is read from its shared-memory copy (SS MMA, the copy the dQ MMA needs anyway) and dQ is issued
+// BEFORE dK, so the drain of dQ — and with it dP of the next q block, which reuses the TMEM region — starts a whole MMA
+// earlier and no dS^T has to be stored to TMEM;  0 = round-1 order (dK with dS^T from TMEM, then dQ).
+#ifndef FFA_BWD_DK_SS
+#define FFA_BWD_DK_SS 1
+#endif
 static_assert(256 * FFA_BWD_REGS_COMPUTE + 128 * FFA_BWD_REGS_DRAIN + 128 * FFA_BWD_REGS_OTHER <= 65536, "register budget");
 // (measured and rejected, round 2: draining dQ straight from registers with sector-coalesced red.global.add.v2.f32 —
 //  tcgen05.ld.16x256b fragments, four lanes per 32-byte sector, no shared-memory staging — is 29 % SLOWER than the
@@ -85,7 +91,7 @@ template <int kD> struct Cfg {
                             kSmemLse = kSmemDQ + 2 * kDQChunkBytes, kSmemDelta = kSmemLse + 1024,
                             kSmemBar = kSmemDelta + 1024, kSmemBytes = kSmemBar + 256;
 };
-constexpr int kBarKV = 0, kBarQFull = 1, kBarQEmpty = 3, kBarDOFull = 5, kBarDOEmpty = 6, kBarS = 9, kBarDP = 10,
+constexpr int kBarKV = 0, kBarQFull = 1, kBarQEmpty = 3, kBarDOFull = 5, kBarDOEmpty = 6, kBarDSFree = 7, kBarS = 9, kBarDP = 10,
               kBarP = 11, kBarDS = 12, kBarDQ = 13, kBarDrained = 14, kBarDKV = 15, kNumBars = 16;
 constexpr uint32_t kTmemS = 0, kTmemDP = 128, kTmemDV = 256, kTmemDK = 384;
 }  // namespace bwd
@@ -301,7 +307,8 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mbar_wait(bar(kBarDP), it & 1);
           tc_fence_after();
           if (wid == 0) FFA_TRB(1, it, 3);
-          if (it > 0) mbar_wait(bar(kBarDQ), (it - 1) & 1);  // previous dQ MMA has finished reading sdS
+          // the MMAs that read the previous dS^T copy in shared memory have retired
+          if (it > 0) mbar_wait(bar(FFA_BWD_DK_SS ? kBarDSFree : kBarDQ), (it - 1) & 1);
           if (wid == 0) FFA_TRB(1, it, 4);
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {
@@ -319,7 +326,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               pk[j * 2] = pack2<kBF16>(ds[0], ds[1]);
               pk[j * 2 + 1] = pack2<kBF16>(ds[2], ds[3]);
             }
-            tmem_st16(tDP + ch * 16, pk);
+            if (!FFA_BWD_DK_SS) tmem_st16(tDP + ch * 16, pk);
 #pragma unroll
             for (int j = 0; j < ((FFA_BWD_ABL & 16) ? 0 : 4); ++j) {
               const int chunk = ch * 4 + j;  // 16-byte chunk (8 q values) inside this thread's 128-byte row
@@ -327,7 +334,7 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                   make_uint4(pk[j * 4], pk[j * 4 + 1], pk[j * 4 + 2], pk[j * 4 + 3]);
             }
           }
-          tc_wait_st();
+          if (!FFA_BWD_DK_SS) tc_wait_st();
           tc_fence_before();
           fence_proxy_async_smem();
           mbar_arrive(bar(kBarDS));
@@ -529,12 +536,21 @@ ffa_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_wait(bar(kBarDS), it & 1);
             tc_fence_after();
             FFA_TRB(0, it, 3);
-            mma_tmemA(tDK, tDP, sQ, it > 0, bar(kBarQEmpty + st));
+            if (!FFA_BWD_DK_SS) mma_tmemA(tDK, tDP, sQ, it > 0, bar(kBarQEmpty + st));
             if (elect_one()) {
 #pragma unroll
               for (uint32_t kk = 0; kk < ((FFA_BWD_ABL & 4) ? 0 : 8); ++kk)
                 mma_ss(tDP, smem_desc(mn_hi, sDS + kk * 2048), smem_desc(mn_hi, sK + kk * 2048), id_mm, kk > 0 ? 1u : 0u);
               tc_commit(bar(kBarDQ));
+              if (FFA_BWD_DK_SS) {
+                // dK += dS^T Q with dS^T [128 kv x 128 q] read K-major from the same shared-memory tile (contraction over q)
+#pragma unroll
+                for (uint32_t kk = 0; kk < 8; ++kk)
+                  mma_ss(tDK, smem_desc(DESC_KMAJOR, sDS + (kk >> 2) * kBoxBytes + (kk & 3) * 32), smem_desc(mn_hi, sQ + kk * 2048),
+                         id_tm, (it > 0 || kk > 0) ? 1u : 0u);
+                tc_commit(bar(kBarQEmpty + st));
+                tc_commit(bar(kBarDSFree));
+              }
             }
             __syncwarp();
             // dP_{it+1} once the dQ tile has been drained out of the shared TMEM region

@@ -73,8 +73,13 @@ __host__ __device__ __forceinline__ size_t plan_entries_off(int n_tiles) {
   size_t o = kPlanHeaderInts + size_t(n_tiles) + 1;
   return (o + 63) & ~size_t(63);
 }
+// Worst case one entry per (tile, slice); capped at kPlanMaxEntries (128 MiB of ids): a mask that overflows the cap sets
+// the overflow flag and the kernels fall back to scanning every slice per tile (correct, slower) instead of asking the
+// caller for an unbounded workspace.
+constexpr size_t kPlanMaxEntries = size_t(32) << 20;
 __host__ __device__ __forceinline__ size_t plan_bytes(int n_tiles, int num_slices) {
   size_t cap = size_t(n_tiles) * size_t(num_slices > 0 ? num_slices : 1);
+  if (cap > kPlanMaxEntries) cap = kPlanMaxEntries;
   return (plan_entries_off(n_tiles) + cap) * sizeof(int);
 }
 

@@ -177,7 +177,7 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     mbar_init(bar(kBarQ), 1);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(bar(kBarFull + i), 1);
-      mbar_init(bar(kBarEmpty + i), 2);  // released by both MMA warps (one per q tile)
+      mbar_init(bar(kBarEmpty + i), 1);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar(kBarS + t), 1);
@@ -332,7 +332,8 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int o = 16; o > 0; o >>= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
       if (lane == 0 && mt != -INFINITY) {
         const float val = mt * args.scale;
-        if (val >= 0.f) atomicMax(reinterpret_cast<int*>(args.max_logits + hq), __float_as_int(val));
+        // ordered-int trick keyed on the SIGN BIT (not on val >= 0: -0.0 compares >= 0 but is INT_MIN as an int)
+        if (!signbit(val)) atomicMax(reinterpret_cast<int*>(args.max_logits + hq), __float_as_int(val));
         else atomicMin(reinterpret_cast<unsigned int*>(args.max_logits + hq), __float_as_uint(val));
       }
     }
@@ -435,104 +436,104 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   } else {
     // register pool = 384 threads x 168 regs (launch bounds) = 64512 = 256 x 208 + 128 x 88
     setmaxnreg_dec<88>();
-    if (wid == 8 || wid == 10) {
-      // =========================== MMA issuers: one warp per q tile ===========================
-      // Warp 8 issues every tcgen05.mma of tile 0, warp 10 those of tile 1.  Each tile is a serial chain
-      // S(b) -> softmax -> PV(b) -> S(b+1); with one issuing warp per chain a wait of one tile (P not ready yet) never
-      // holds back MMAs of the other tile that could already run — the tensor pipe interleaves the two streams by
-      // itself.  (A single issuing warp left the pipe idle ~1000 of 3200 clocks per kv block: measured with the
-      // -DFFA_TRACE timeline, profiles/r02_trace.txt.)  The whole warp runs the loop with warp-uniform control flow
-      // (descriptors live in uniform registers); only tcgen05.mma / tcgen05.commit are issued by one elected lane.
-      // K/V ring buffers are released by BOTH warps (empty barriers count 2): a tcgen05.commit after the last MMA that
-      // reads the buffer, or a plain arrive when this tile skips the block (after waiting for the fill, which bounds the
-      // run-ahead of a warp to the ring depth).
-      const int t = wid == 8 ? 0 : 1;
+    if (wid == 8) {
+      // =========================== MMA issuer ===========================
+      // ONE warp issues the MMAs of both q tiles in the fixed order PV0 S0 PV1 S1: that order staggers the two tiles (the
+      // softmax of one overlaps the MMAs of the other).  A variant with one issuing warp per tile was measured 18 % SLOWER
+      // (round 2): the two chains fall into lock-step, both softmax phases then share the MUFU and the pipe idles.
+      // The whole warp runs this loop with warp-uniform control flow (descriptors live in uniform registers);
+      // only the tcgen05.mma / tcgen05.commit instructions themselves are issued by one elected lane.
       constexpr uint32_t idesc_s = make_idesc(kBF16, false, false, 128, 128);
       constexpr uint32_t idesc_pv = make_idesc(kBF16, false, true, 128, kD);  // O tile is 128 x kD
       constexpr uint64_t desc_v_hi = desc_mnmajor(kBoxBytes);
-      const uint32_t sQ = smem_base + kSmemQ + t * kTileBytes, sKV = smem_base + kSmemKV;
-      const uint32_t tSt = tmem + kTmemS + t * 128, tOt = tmem + kTmemO + t * 128;
-      uint32_t n_act = 0;        // active blocks issued so far for this tile
-      bool has_prev = false;     // a PV of this tile is pending
-      uint32_t prev_load = 0;    // ring load index of the V block of the pending PV
-      uint32_t blk = 0;          // kv block counter (ring: K = 2*blk, V = 2*blk+1)
+      const uint32_t sQ = smem_base + kSmemQ, sKV = smem_base + kSmemKV;
+      uint32_t n_act0 = 0, n_act1 = 0;            // active blocks issued so far per tile
+      bool has_prev0 = false, has_prev1 = false;  // a PV of that tile is pending
+      uint32_t prev_load0 = 0, prev_load1 = 0;    // ring load index of the V block of the pending PV
+      uint32_t pend = 0;                          // outstanding PV users per ring buffer, 4 bits each
+      uint32_t blk = 0;                           // kv block counter (ring: K = 2*blk, V = 2*blk+1)
       bool q_ready = false;
 
-      auto issue_pv = [&]() {
-        const uint32_t buf = prev_load % kStages;
+      auto issue_pv = [&](const int t, const uint32_t n_act_t, const uint32_t li) {
+        const uint32_t buf = li % kStages;
         const uint32_t sV = sKV + buf * kTileBytes;
-        FFA_TR(0, n_act - 1, 4 * t + 0);
-        mbar_wait(bar(kBarFull + buf), (prev_load / kStages) & 1);
-        mbar_wait(bar(kBarP + t), (n_act - 1) & 1);  // first 64 columns of P_t are in TMEM
+        const uint32_t tP = tmem + kTmemS + t * 128, tOt = tmem + kTmemO + t * 128;
+        FFA_TR(0, n_act_t - 1, 4 * t + 0);
+        mbar_wait(bar(kBarFull + buf), (li / kStages) & 1);
+        mbar_wait(bar(kBarP + t), (n_act_t - 1) & 1);  // first 64 columns of P_t are in TMEM
         tc_fence_after();
-        FFA_TR(0, n_act - 1, 4 * t + 1);
+        FFA_TR(0, n_act_t - 1, 4 * t + 1);
         if (elect_one()) {
 #pragma unroll
           for (uint32_t kk = 0; kk < ((FFA_FWD_ABL & 32) ? 0 : 4); ++kk)
-            mma_ts(tOt, tSt + kk * 8, smem_desc(desc_v_hi, sV + kk * 2048), idesc_pv, (n_act > 1 || kk > 0) ? 1u : 0u);
+            mma_ts(tOt, tP + kk * 8, smem_desc(desc_v_hi, sV + kk * 2048), idesc_pv, (n_act_t > 1 || kk > 0) ? 1u : 0u);
         }
         __syncwarp();
-        mbar_wait(bar(kBarPhi + t), (n_act - 1) & 1);  // second half
+        mbar_wait(bar(kBarPhi + t), (n_act_t - 1) & 1);  // second half
         tc_fence_after();
-        FFA_TR(0, n_act - 1, 4 * t + 2);
+        FFA_TR(0, n_act_t - 1, 4 * t + 2);
+        pend -= 1u << (4 * buf);
+        const bool release = ((pend >> (4 * buf)) & 15u) == 0;
         if (elect_one()) {
 #pragma unroll
           for (uint32_t kk = 4; kk < ((FFA_FWD_ABL & 32) ? 0 : 8); ++kk)
-            mma_ts(tOt, tSt + kk * 8, smem_desc(desc_v_hi, sV + kk * 2048), idesc_pv, 1u);
-          tc_commit(bar(kBarEmpty + buf));  // this tile is done with the V block
+            mma_ts(tOt, tP + kk * 8, smem_desc(desc_v_hi, sV + kk * 2048), idesc_pv, 1u);
+          if (release) tc_commit(bar(kBarEmpty + buf));
         }
         __syncwarp();
+      };
+      auto issue_s = [&](const int t, const uint32_t sK) {
+        const uint32_t tSt = tmem + kTmemS + t * 128;
+        if (elect_one()) {
+#pragma unroll
+          for (uint32_t kk = 0; kk < ((FFA_FWD_ABL & 64) ? 0 : kD / 16); ++kk) {  // contraction over the head dim
+            const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
+            mma_ss(tSt, smem_desc(DESC_KMAJOR, sQ + t * kTileBytes + off), smem_desc(DESC_KMAJOR, sK + off), idesc_s,
+                   kk > 0 ? 1u : 0u);
+          }
+          tc_commit(bar(kBarS + t));
+        }
+        __syncwarp();
+        FFA_TR(0, (t == 0 ? n_act0 : n_act1), 4 * t + 3);  // S of block n_act (0-based) issued
       };
 
       SliceCursor cur;
       cur.init(args.meta, args.plan, tile);
       Slice sl;
       CtaGeom g;
-      TileGeom tg;
+      TileGeom tg0, tg1;
       while (cur.next(sl)) {
         if (!g.init(sl, R0)) continue;
-        tg.init(sl, R0 + t * kBlockM);
+        tg0.init(sl, R0);
+        tg1.init(sl, R0 + kBlockM);
         for (int b = 0; b < g.nblk; ++b, ++blk) {
           const int bs = g.c_min + b * kBlockN;
-          const bool act = tg.active(bs);
+          const bool a0 = tg0.active(bs), a1 = tg1.active(bs);
           if (!q_ready) {
             mbar_wait(bar(kBarQ), 0);
             q_ready = true;
           }
           const uint32_t lk = 2 * blk, kbuf = lk % kStages, lv = lk + 1, vbuf = lv % kStages;
-          if (has_prev) { issue_pv(); has_prev = false; }
           mbar_wait(bar(kBarFull + kbuf), (lk / kStages) & 1);
           tc_fence_after();
-          if (act) {
-            const uint32_t sK = sKV + kbuf * kTileBytes;
-            if (elect_one()) {
-#pragma unroll
-              for (uint32_t kk = 0; kk < ((FFA_FWD_ABL & 64) ? 0 : kD / 16); ++kk) {  // contraction over the head dim
-                const uint32_t off = (kk >> 2) * kBoxBytes + (kk & 3) * 32;
-                mma_ss(tSt, smem_desc(DESC_KMAJOR, sQ + off), smem_desc(DESC_KMAJOR, sK + off), idesc_s, kk > 0 ? 1u : 0u);
-              }
-              tc_commit(bar(kBarS + t));
-              tc_commit(bar(kBarEmpty + kbuf));  // this tile is done with the K block once its S MMAs retire
-            }
-            __syncwarp();
-            FFA_TR(0, n_act, 4 * t + 3);
-            has_prev = true;
-            prev_load = lv;
-            ++n_act;
-          } else {
-            // block not visible from this tile: hand both buffers back (after their fills: bounds the run-ahead)
-            mbar_wait(bar(kBarFull + vbuf), (lv / kStages) & 1);
-            if (elect_one()) {
-              mbar_arrive(bar(kBarEmpty + kbuf));
-              mbar_arrive(bar(kBarEmpty + vbuf));
-            }
-            __syncwarp();
+          pend = (pend & ~(15u << (4 * vbuf))) | (((a0 ? 1u : 0u) + (a1 ? 1u : 0u)) << (4 * vbuf));
+          const uint32_t sK = sKV + kbuf * kTileBytes;
+          if (has_prev0) { issue_pv(0, n_act0, prev_load0); has_prev0 = false; }
+          if (a0) { issue_s(0, sK); has_prev0 = true; prev_load0 = lv; ++n_act0; }
+          if (has_prev1) { issue_pv(1, n_act1, prev_load1); has_prev1 = false; }
+          if (a1) { issue_s(1, sK); has_prev1 = true; prev_load1 = lv; ++n_act1; }
+          if (elect_one()) {
+            tc_commit(bar(kBarEmpty + kbuf));  // K block free once both S MMAs retire
+            if (((pend >> (4 * vbuf)) & 15u) == 0) tc_commit(bar(kBarEmpty + vbuf));  // V block nobody needs
           }
+          __syncwarp();
         }
       }
-      if (has_prev) issue_pv();
+      if (has_prev0) issue_pv(0, n_act0, prev_load0);
+      if (has_prev1) issue_pv(1, n_act1, prev_load1);
       if (elect_one()) {
-        if (n_act > 0) tc_commit(bar(kBarO + t));
+        if (n_act0 > 0) tc_commit(bar(kBarO + 0));
+        if (n_act1 > 0) tc_commit(bar(kBarO + 1));
       }
       __syncwarp();
     } else if (wid == 9) {
