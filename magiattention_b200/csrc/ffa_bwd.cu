@@ -46,11 +46,12 @@
 #ifndef FFA_BWD_REGS_OTHER
 #define FFA_BWD_REGS_OTHER 72
 #endif
-// dK operand source: 1 = dS^T is read from its shared-memory copy (SS MMA, the copy the dQ MMA needs anyway) and dQ is issued
-// BEFORE dK, so the drain of dQ — and with it dP of the next q block, which reuses the TMEM region — starts a whole MMA
-// earlier and no dS^T has to be stored to TMEM;  0 = round-1 order (dK with dS^T from TMEM, then dQ).
+// dK operand source: 0 (default) = dS^T from TMEM (TS MMA), dK before dQ;  1 = dS^T read from its shared-memory copy (SS MMA)
+// with dQ issued BEFORE dK so that its drain starts a whole MMA earlier.  Measured equal-to-slightly-slower (round 2, causal
+// 32K x 8 heads: 4.42 ms vs 4.38 ms): once the TMEM region is released before staging, the loop is bound by the dQ
+// reduce path itself (st.shared staging + TMA reduce-add ~ 770 clocks per 16 KB chunk), not by the MMA order.
 #ifndef FFA_BWD_DK_SS
-#define FFA_BWD_DK_SS 1
+#define FFA_BWD_DK_SS 0
 #endif
 static_assert(256 * FFA_BWD_REGS_COMPUTE + 128 * FFA_BWD_REGS_DRAIN + 128 * FFA_BWD_REGS_OTHER <= 65536, "register budget");
 // (measured and rejected, round 2: draining dQ straight from registers with sector-coalesced red.global.add.v2.f32 —
