@@ -1,3 +1,9 @@
+// EXPERIMENT, NOT BUILT (tools/experimental): the forward kernel with the opt-in "split-row" layout (template flag kSplit:
+// four softmax warpgroups = (q tile, column half), two threads per q row exchanging block maxima through shared memory, so
+// that the fixed latencies of one warp hide behind the MUFU work of its sibling on the same SM sub-partition).  State at the
+// end of round 2: compiles; after fixing the register-pool over-subscription (setmaxnreg only redistributes the launch
+// allocation: 640 x 96 = 61440 registers = 512 x 104 + 128 x 64) the first three ladder cases pass and a later one (GQA /
+// ragged) still hangs, with no GPU budget left to debug it.  The product kernel is magiattention_b200/csrc/ffa_fwd.cu.
 // ffa_fwd.cu — flex-flash-attention FORWARD for sm_100a (tcgen05 + TMEM + TMA).
 //
 // Replaces the reference's Hopper-only FFA forward (csrc/flexible_flash_attention/
@@ -24,6 +30,7 @@
 //    the reference does with a separate Triton pass (functional/utils.py:467-558) — and stores rows.
 #include <cuda.h>
 #include <cmath>
+#include <cstdlib>
 #include <type_traits>
 #include "ffa_common.cuh"
 #include "ffa_args.h"
@@ -56,20 +63,32 @@ namespace ffa {
 using namespace sm100;
 
 namespace fwd {
+// Two forward layouts share this file (template flag kSplit):
+//   kSplit = false  384 threads: one softmax thread per q row (two warpgroups, one per 128-row tile), 5-deep K/V ring;
+//   kSplit = true   640 threads: TWO softmax threads per q row (four warpgroups: tile x column half), each owning 64 of a
+//                   kv block's 128 score columns; the halves exchange their block maxima through shared memory.  Two warps
+//                   of the same tile then share every SM sub-partition, so the fixed latencies of one (TMEM load / store
+//                   waits, barrier hand-offs) hide behind the MUFU work of the other.  4-deep K/V ring (pays for the
+//                   exchange buffers).
 constexpr int kThreads = 384;
+constexpr int kThreadsSplit = 640;  // 16 softmax warps + MMA warp + TMA warp + 2 idle (setmaxnreg works on whole warpgroups)
 constexpr int kStages = 5;
+constexpr int kStagesSplit = 4;
 constexpr uint32_t kBoxBytes = 128 * 64 * 2;  // one TMA box: 128 rows x 64 columns of 16-bit elements
 // operand tiles are 128 rows x kD columns = kD/64 boxes; smem map: [Q0 Q1][K/V ring of kStages tiles][barriers]
-template <int kD> struct Cfg {
+template <int kD, bool kSplit = false> struct Cfg {
   static_assert(kD == 64 || kD == 128, "head_dim must be 64 or 128");
+  static constexpr int kNumStages = kSplit ? kStagesSplit : kStages;
   static constexpr uint32_t kBoxes = kD / 64;
   static constexpr uint32_t kTileBytes = kBoxes * kBoxBytes;
   static constexpr uint32_t kSmemQ = 0;
   static constexpr uint32_t kSmemKV = 2 * kTileBytes;
-  static constexpr uint32_t kSmemBar = kSmemKV + kStages * kTileBytes;
-  static constexpr uint32_t kSmemBytes = kSmemBar + 256;
+  static constexpr uint32_t kSmemBar = kSmemKV + kNumStages * kTileBytes;
+  static constexpr uint32_t kSmemXch = kSmemBar + 256;  // kSplit: [parity][tile][half][128] fp32 block maxima / row sums
+  static constexpr uint32_t kSmemBytes = kSmemXch + (kSplit ? 2 * 2 * 2 * 128 * 4 : 0);
 };
 // barrier indices
+// (laid out for the deeper ring; the 4-stage layout simply leaves two slots unused)
 constexpr int kBarQ = 0, kBarFull = 1, kBarEmpty = kBarFull + kStages, kBarS = kBarEmpty + kStages, kBarP = kBarS + 2,
               kBarPhi = kBarP + 2, kBarO = kBarPhi + 2, kNumBars = kBarO + 2;  // kBarP: first half of P, kBarPhi: second
 static_assert(kNumBars * 8 + 8 <= 256, "barrier area");
@@ -143,13 +162,17 @@ __device__ __forceinline__ float2 softmax_quarter(const uint32_t* sr, float sl2,
   return __fadd2_rn(a01, a23);
 }
 
-template <int kD, bool kBF16, bool kOutF32, bool kMaxLogits>
-__global__ void __launch_bounds__(fwd::kThreads, 1)
+template <int kD, bool kBF16, bool kOutF32, bool kMaxLogits, bool kSplit>
+__global__ void __launch_bounds__(kSplit ? fwd::kThreadsSplit : fwd::kThreads, 1)
 ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const FwdArgs args) {
   using namespace fwd;
-  constexpr uint32_t kTileBytes = Cfg<kD>::kTileBytes, kBoxes = Cfg<kD>::kBoxes;
-  constexpr uint32_t kSmemQ = Cfg<kD>::kSmemQ, kSmemKV = Cfg<kD>::kSmemKV, kSmemBar = Cfg<kD>::kSmemBar;
+  using C = Cfg<kD, kSplit>;
+  constexpr uint32_t kTileBytes = C::kTileBytes, kBoxes = C::kBoxes;
+  constexpr uint32_t kSmemQ = C::kSmemQ, kSmemKV = C::kSmemKV, kSmemBar = C::kSmemBar;
+  constexpr int kStages = C::kNumStages;              // shadows fwd::kStages: ring depth of this layout
+  constexpr int kSmWarps = kSplit ? 16 : 8;           // softmax warps
+  constexpr int kMmaWarp = kSmWarps, kTmaWarp = kSmWarps + 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = smem_u32(smem);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemBar + kNumBars * 8);
@@ -187,11 +210,11 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     fence_barrier_init();
   }
-  if (wid == 8) {
+  if (wid == kMmaWarp) {
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
-  if (wid == 9 && lane == 0) {
+  if (wid == kTmaWarp && lane == 0) {
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmK);
     prefetch_tmap(&tmV);
@@ -201,7 +224,213 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (wid < 8) {
+  if constexpr (kSplit) {
+   if (wid < kSmWarps) {
+    // =========================== softmax: four warpgroups = (tile, column half) ===========================
+    setmaxnreg_inc<104>();
+    const int grp = wid >> 2, t = grp >> 1, hf = grp & 1;
+    const int row_in_tile = (wid & 3) * 32 + lane;  // TMEM lane
+    const int row = R0 + t * kBlockM + row_in_tile;
+    const uint32_t lane_off = uint32_t((wid & 3) * 32) << 16;
+    const uint32_t tS = tmem + lane_off + kTmemS + t * 128 + hf * 64;   // my 64 score columns
+    const uint32_t tP = tmem + lane_off + kTmemS + t * 128 + hf * 32;   // my 32 packed P columns
+    const uint32_t tO = tmem + lane_off + kTmemO + t * 128 + hf * (kD / 2);
+    const float sl2 = args.scale * 1.4426950408889634f;
+    float* xch = reinterpret_cast<float*>(smem + C::kSmemXch);
+    auto xslot = [&](int parity, int half) -> float* { return xch + ((parity * 2 + t) * 2 + half) * 128 + row_in_tile; };
+
+    float m_ref = -INFINITY, l_sum = 0.f, m_true = -INFINITY;
+    uint32_t n_act = 0;
+    SliceCursor cur;
+    cur.init(args.meta, args.plan, tile);
+    Slice sl;
+    CtaGeom g;
+    TileGeom tg;
+    while (cur.next(sl)) {
+      if (!g.init(sl, R0)) continue;
+      tg.init(sl, R0 + t * kBlockM);
+      const bool row_in = (row >= sl.q0) && (row < sl.q1);
+      const int lo_r = row_in ? sl.lo(row) : 0;
+      const int hi_r = row_in ? min(sl.hi(row), sl.k1) : 0;  // empty range when row not in slice
+      for (int b = 0; b < g.nblk; ++b) {
+        const int bs = g.c_min + b * kBlockN;
+        if (!tg.active(bs)) continue;
+        mbar_wait(bar(kBarS + t), n_act & 1);
+        tc_fence_after();
+        uint32_t sr[64];
+        tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+        tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+        tc_wait_ld();
+        if (!tg.full(bs)) {
+          const int lo_rel = lo_r - bs - hf * 64, hi_rel = hi_r - bs - hf * 64;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            int lo_c = min(max(lo_rel - c * 32, 0), 32), hi_c = min(max(hi_rel - c * 32, 0), 32);
+            uint32_t m_hi = hi_c >= 32 ? 0xffffffffu : ((1u << hi_c) - 1u);
+            uint32_t m_lo = lo_c >= 32 ? 0xffffffffu : ((1u << lo_c) - 1u);
+            uint32_t bits = m_hi & ~m_lo;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!((bits >> i) & 1u)) sr[c * 32 + i] = 0xff800000u;  // -inf
+          }
+        }
+        float mb;
+        {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < 64; i += 8) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              m4[j] = fmaxf(m4[j], fmaxf(__uint_as_float(sr[i + 2 * j]), __uint_as_float(sr[i + 2 * j + 1])));
+          }
+          mb = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        }
+        *xslot(n_act & 1, hf) = mb;  // my half's block maximum of this row
+        // first 32 exponentials on the stale reference while the other half's maximum travels
+        float mneg = (m_ref == -INFINITY) ? 0.f : -m_ref * sl2;
+        uint32_t pr[16];
+        float2 a0 = softmax_quarter<kBF16, true>(&sr[0], sl2, mneg, pr);
+        named_bar_sync(1 + t, 256);  // also: both halves hold their S columns in registers => P may overwrite the S region
+        tmem_st16(tP, pr);
+        mb = fmaxf(mb, *xslot(n_act & 1, hf ^ 1));
+        if constexpr (kMaxLogits) m_true = fmaxf(m_true, mb);
+        const float m_new = fmaxf(m_ref, mb);
+        const bool upd = (m_new - m_ref) * sl2 > kRescaleThreshold;  // identical in both halves of the row
+        if (__any_sync(0xffffffffu, upd)) {
+          float corr = 1.f;
+          if (upd) {
+            corr = (m_ref == -INFINITY) ? 0.f : ex2((m_ref - m_new) * sl2);
+            m_ref = m_new;
+            l_sum *= corr;
+          }
+          if (n_act > 0) {  // rescale my half of the O columns (PV of the previous block has completed, see above)
+#pragma unroll
+            for (int c = 0; c < kD / 64; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tO + c * 32, o);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * corr);
+              tmem_st32(tO + c * 32, o);
+            }
+          }
+          mneg = (m_ref == -INFINITY) ? 0.f : -m_ref * sl2;
+          a0 = softmax_quarter<kBF16, true>(&sr[0], sl2, mneg, pr);
+          tmem_st16(tP, pr);
+        }
+        const float2 a1 = softmax_quarter<kBF16, false>(&sr[32], sl2, mneg, pr);
+        tmem_st16(tP + 16, pr);
+        l_sum += (a0.x + a0.y) + (a1.x + a1.y);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar((hf == 0 ? kBarP : kBarPhi) + t));  // my half of P (= PV k-steps 4*hf .. 4*hf+3) is in TMEM
+        ++n_act;
+      }
+    }
+    // ------------------------------- epilogue (split) -------------------------------
+    if constexpr (kMaxLogits) {
+      float mt = m_true;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+      if (lane == 0 && mt != -INFINITY && hf == 0) {
+        const float val = mt * args.scale;
+        if (!signbit(val)) atomicMax(reinterpret_cast<int*>(args.max_logits + hq), __float_as_int(val));
+        else atomicMin(reinterpret_cast<unsigned int*>(args.max_logits + hq), __float_as_uint(val));
+      }
+    }
+    const bool row_ok = row < args.total_q;
+    float* lse_ptr = args.lse + int64_t(row) * args.lse_stride_t + int64_t(hq) * args.lse_stride_h;
+    const float lse_old = (args.accumulate && row_ok) ? *lse_ptr : -INFINITY;  // read before the other half may write it
+    // the slot of parity n_act was last read two blocks ago: free for the row-sum exchange
+    *xslot(n_act & 1, hf) = l_sum;
+    named_bar_sync(1 + t, 256);
+    l_sum += *xslot(n_act & 1, hf ^ 1);
+    const bool dead = (n_act == 0) || (m_ref == -INFINITY) || !(l_sum > 0.f);
+    float lse_new = dead ? -INFINITY : fmaf(m_ref, args.scale, __logf(l_sum));
+    float w_new = dead ? 0.f : 1.f / l_sum;
+    float w_old = 0.f;
+    bool need_old = false;
+    if (lse_old != -INFINITY) {
+      need_old = true;
+      if (dead) {
+        w_old = 1.f;
+        lse_new = lse_old;
+      } else {
+        const float mx = fmaxf(lse_old, lse_new), mn = fminf(lse_old, lse_new);
+        const float lse_m = mx + log1pf(__expf(mn - mx));
+        w_old = __expf(lse_old - lse_m);
+        w_new *= __expf(lse_new - lse_m);
+        lse_new = lse_m;
+      }
+    }
+    if (n_act > 0) {
+      mbar_wait(bar(kBarO + t), 0);
+      tc_fence_after();
+    }
+    using OutT = typename std::conditional<kOutF32, float, typename std::conditional<kBF16, __nv_bfloat16, __half>::type>::type;
+    OutT* orow = reinterpret_cast<OutT*>(args.out) + int64_t(row) * args.o_stride_t + int64_t(hq) * args.o_stride_h + hf * (kD / 2);
+    const bool skip_store = !row_ok || (args.accumulate && dead && need_old);  // nothing new: keep the old partial
+#pragma unroll
+    for (int c = 0; c < kD / 64; ++c) {
+      float o[32];
+      if (n_act > 0 && !dead) {
+        uint32_t r[32];
+        tmem_ld32(tO + c * 32, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]) * w_new;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
+      }
+      if (!skip_store) {
+        if constexpr (kOutF32) {
+          float4* dst = reinterpret_cast<float4*>(orow + c * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 x = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            if (need_old) {
+              float4 y = dst[i];
+              x.x = fmaf(w_old, y.x, x.x); x.y = fmaf(w_old, y.y, x.y);
+              x.z = fmaf(w_old, y.z, x.z); x.w = fmaf(w_old, y.w, x.w);
+            }
+            dst[i] = x;
+          }
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = o[8 * i + j];
+            if (need_old) {
+              uint4 y = dst[i];
+              const uint32_t yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float lo, hi;
+                if constexpr (kBF16) {
+                  lo = __uint_as_float(yw[j] << 16);
+                  hi = __uint_as_float(yw[j] & 0xffff0000u);
+                } else {
+                  __half2 h2 = *reinterpret_cast<const __half2*>(&yw[j]);
+                  lo = __low2float(h2);
+                  hi = __high2float(h2);
+                }
+                x[2 * j] = fmaf(w_old, lo, x[2 * j]);
+                x[2 * j + 1] = fmaf(w_old, hi, x[2 * j + 1]);
+              }
+            }
+            dst[i] = make_uint4(pack2<kBF16>(x[0], x[1]), pack2<kBF16>(x[2], x[3]), pack2<kBF16>(x[4], x[5]),
+                                pack2<kBF16>(x[6], x[7]));
+          }
+        }
+      }
+    }
+    if (!skip_store && hf == 0) *lse_ptr = lse_new;
+   }
+  }
+  if (!kSplit && wid < 8) {
     // =========================== softmax warpgroups ===========================
     setmaxnreg_inc<208>();
     const int t = wid >> 2;                        // MMA tile 0/1
@@ -433,10 +662,13 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     }
     if (!skip_store) *lse_ptr = lse_new;
-  } else {
-    // register pool = 384 threads x 168 regs (launch bounds) = 64512 = 256 x 208 + 128 x 88
-    setmaxnreg_dec<88>();
-    if (wid == 8) {
+  }
+  if (wid >= kSmWarps) {
+    // register pool: 384 threads x 168 regs (launch bounds) = 64512 = 256 x 208 + 128 x 88;  split layout: 640 threads x 96
+    // at launch = 61440 registers in the CTA pool (setmaxnreg only redistributes what the launch allocated), 512 x 104 +
+    // 128 x 64 = 61440 after the moves
+    if constexpr (kSplit) setmaxnreg_dec<64>(); else setmaxnreg_dec<88>();
+    if (wid == kMmaWarp) {
       // =========================== MMA issuer ===========================
       // ONE warp issues the MMAs of both q tiles in the fixed order PV0 S0 PV1 S1: that order staggers the two tiles (the
       // softmax of one overlaps the MMAs of the other).  A variant with one issuing warp per tile was measured 18 % SLOWER
@@ -536,7 +768,7 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (n_act1 > 0) tc_commit(bar(kBarO + 1));
       }
       __syncwarp();
-    } else if (wid == 9) {
+    } else if (wid == kTmaWarp) {
       // =========================== TMA producer (warp-uniform loop, one elected lane issues) ===========
       const uint32_t sQ = smem_base + kSmemQ, sKV = smem_base + kSmemKV;
       uint32_t blk = 0;
@@ -587,25 +819,44 @@ ffa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (wid == 8) tmem_dealloc(tmem, 512);
+  if (wid == kMmaWarp) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------
-template <int kD, bool kBF16, bool kOutF32, bool kMaxLogits>
-static cudaError_t launch_one(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
-                              const FwdArgs& a, int grid, cudaStream_t stream) {
-  auto kern = ffa_fwd_kernel<kD, kBF16, kOutF32, kMaxLogits>;
-  constexpr uint32_t smem_bytes = fwd::Cfg<kD>::kSmemBytes;
+// B200_FFA_FWD_SPLIT=1 selects the four-warpgroup layout (two softmax threads per row); default: see kDefaultSplit
+#ifndef FFA_FWD_DEFAULT_SPLIT
+#define FFA_FWD_DEFAULT_SPLIT 0
+#endif
+static bool use_split() {
+  static const int v = [] {
+    const char* e = getenv("B200_FFA_FWD_SPLIT");
+    return e ? atoi(e) : FFA_FWD_DEFAULT_SPLIT;
+  }();
+  return v != 0;
+}
+
+template <int kD, bool kBF16, bool kOutF32, bool kMaxLogits, bool kSplit>
+static cudaError_t launch_one_s(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                                const FwdArgs& a, int grid, cudaStream_t stream) {
+  auto kern = ffa_fwd_kernel<kD, kBF16, kOutF32, kMaxLogits, kSplit>;
+  constexpr uint32_t smem_bytes = fwd::Cfg<kD, kSplit>::kSmemBytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, fwd::kThreads, smem_bytes, stream>>>(tmQ, tmK, tmV, a);
+  kern<<<grid, kSplit ? fwd::kThreadsSplit : fwd::kThreads, smem_bytes, stream>>>(tmQ, tmK, tmV, a);
   return cudaGetLastError();
+}
+
+template <int kD, bool kBF16, bool kOutF32, bool kMaxLogits>
+static cudaError_t launch_one(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                              const FwdArgs& a, int grid, cudaStream_t stream) {
+  return use_split() ? launch_one_s<kD, kBF16, kOutF32, kMaxLogits, true>(tmQ, tmK, tmV, a, grid, stream)
+                     : launch_one_s<kD, kBF16, kOutF32, kMaxLogits, false>(tmQ, tmK, tmV, a, grid, stream);
 }
 
 template <int kD, bool kMaxLogits>
