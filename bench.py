@@ -472,7 +472,7 @@ def main():
         detail = {}
         for nm, m_, r_ in zip(names, mine, refs):
             r_loc = dispatch(r_.detach(), key).float()
-            d = (m_.float() - r_loc)
+            d = (m_.detach().float() - r_loc)
             ma = float(d.abs().max())
             rel = float(d.norm() / r_loc.norm().clamp_min(1e-12))
             detail[nm] = {"max_abs": ma, "rel_err": rel}
