@@ -1,1 +1,1 @@
-from magiattention_b200.common import AttnForwardMeta, AttnMaskType, AttnOverlapMode, AttnRange, AttnRanges, RangeError  # noqa: F401
+from magiattention_b200.common import AttnForwardMeta, AttnMaskType, AttnOverlapMode, AttnRange, AttnRanges, AttnRole, RangeError  # noqa: F401

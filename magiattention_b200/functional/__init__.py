@@ -23,3 +23,5 @@ try:  # registers torch.ops.flex_flash_attn.* (the reference's torch.compile sea
     from . import custom_ops  # noqa: F401,E402
 except RuntimeError:  # pragma: no cover - the ops were registered by another library in this process
     custom_ops = None
+
+from .fa4 import fa4_bwd, fa4_fwd  # noqa: F401,E402

@@ -39,3 +39,34 @@ def test_slices_area_matches_oracle_mask_area():
     for c in mask_configs(1):
         assert bench.slices_area(c["q_ranges"], c["k_ranges"], c["types"]) == orc.mask_area(c["q_ranges"], c["k_ranges"], c["types"])
     assert bench.slices_area([[0, 4096]], [[0, 4096]], [1]) == bench.causal_area(4096)
+
+
+def test_named_workloads_are_deterministic_and_area_exact():
+    """bench_workloads.make_workload: the five BASELINE configs — fixed slice lists (seed 42), closed-form areas equal to the
+    dense mask areas on reduced sizes, and the C2 sliding-window decomposition equal to the direct definition."""
+    import torch
+
+    from bench_workloads import make_workload, sample_doc_lengths
+    from oracle import ffa_oracle as orc
+
+    assert make_workload("C1")["area"] == 4096 * 4097 // 2 and make_workload("C1")["fwd_only"]
+    assert make_workload("C3")["area"] == 2147516416 and make_workload("C4")["area"] == 34359869440  # SURVEY §8d
+    c5 = make_workload("C5")
+    assert c5["num_slices"] == 1854 and c5["num_heads_q"] == 64 and c5["num_heads_kv"] == 8 and c5["seq_len"] == 1 << 20
+    assert make_workload("C5")["q_ranges"] == c5["q_ranges"]  # deterministic
+    for cfg in ("C2", "C5"):
+        w = make_workload(cfg, seqlen=8192)
+        T = w["seq_len"]
+        m = orc.mask_from_slices(w["q_ranges"], w["k_ranges"], w["types"], T, T)
+        assert int(m.sum()) == w["area"], cfg
+    w = make_workload("C2", seqlen=8192)
+    T, lens = w["seq_len"], sample_doc_lengths(8192, 8192 // 4)
+    ref = torch.zeros(T, T, dtype=torch.bool)
+    i, j, off = torch.arange(T)[:, None], torch.arange(T)[None, :], 0
+    for d, n in enumerate(lens):
+        blk = (i >= off) & (i < off + n) & (j >= off) & (j <= i)
+        if d % 2 == 1:
+            blk &= j >= i - 1024
+        ref |= blk
+        off += n
+    assert torch.equal(orc.mask_from_slices(w["q_ranges"], w["k_ranges"], w["types"], T, T), ref)
