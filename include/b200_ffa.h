@@ -146,6 +146,14 @@ typedef struct {
   float* dsink;
   int32_t seqlen_sink;
   int32_t sink_layout;
+  /* Row statistics shared between calls (NULL = keep them in `workspace`, recomputed every call).  The backward first
+   * reduces (out, dout, lse) to two fp32 vectors per (head, row): delta = rowsum(out o dout) and lse * log2(e).  Under
+   * context parallelism one backward pass makes one call per stage with the SAME out / dout / lse and different K/V, so the
+   * caller may pass a buffer of b200_ffa_bwd_row_stats_bytes(total_q, num_heads_q) bytes (256-byte aligned):
+   * row_stats_ready == 0 computes the statistics into it, != 0 reuses what an earlier call of this pass left there
+   * (stream-ordered).  The reference recomputes them in every stage call (flex_flash_bwd.hpp preprocess). */
+  void* row_stats;
+  int32_t row_stats_ready;
 } b200_ffa_bwd_params;
 
 /* Library / build identification: "b200_ffa <version> sm_100a". */
@@ -155,6 +163,9 @@ B200_API const char* b200_ffa_last_error(void);
 
 B200_API size_t b200_ffa_fwd_workspace_bytes(const b200_ffa_fwd_params* p);
 B200_API size_t b200_ffa_bwd_workspace_bytes(const b200_ffa_bwd_params* p);
+/* size of the optional `row_stats` buffer of b200_ffa_bwd_params */
+B200_API size_t b200_ffa_bwd_row_stats_bytes(int32_t total_q, int32_t num_heads_q);
+size_t b200_ffa_bwd_row_stats_bytes(int32_t total_q, int32_t num_heads_q);
 
 B200_API int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream);
 B200_API int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream);

@@ -66,12 +66,13 @@ class BwdParams(C.Structure):
         ("accumulate_dkv", C.c_int32), ("sm_margin", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("sink", C.c_void_p), ("dsink", C.c_void_p), ("seqlen_sink", C.c_int32), ("sink_layout", C.c_int32),
+        ("row_stats", C.c_void_p), ("row_stats_ready", C.c_int32),
     ]
 
 
 EXPORTS = [
     "b200_ffa_version", "b200_ffa_last_error", "b200_ffa_fwd_workspace_bytes", "b200_ffa_bwd_workspace_bytes",
-    "b200_ffa_fwd", "b200_ffa_bwd", "b200_lse_merge", "b200_sink_merge", "b200_range_reduce_sum", "b200_ffa_last_launch_count",
+    "b200_ffa_fwd", "b200_ffa_bwd", "b200_ffa_bwd_row_stats_bytes", "b200_lse_merge", "b200_sink_merge", "b200_range_reduce_sum", "b200_ffa_last_launch_count",
     "b200_nvl_alloc", "b200_nvl_free", "b200_nvl_export", "b200_nvl_import", "b200_nvl_release", "b200_nvl_copy_spans",
     "b200_nvl_signal", "b200_nvl_wait",
 ]
@@ -98,6 +99,8 @@ def lib() -> C.CDLL:
                 l.b200_ffa_fwd_workspace_bytes.argtypes = [C.POINTER(FwdParams)]
                 l.b200_ffa_bwd_workspace_bytes.restype = C.c_size_t
                 l.b200_ffa_bwd_workspace_bytes.argtypes = [C.POINTER(BwdParams)]
+                l.b200_ffa_bwd_row_stats_bytes.restype = C.c_size_t
+                l.b200_ffa_bwd_row_stats_bytes.argtypes = [C.c_int32, C.c_int32]
                 l.b200_ffa_fwd.restype = C.c_int
                 l.b200_ffa_fwd.argtypes = [C.POINTER(FwdParams), C.c_void_p]
                 l.b200_ffa_bwd.restype = C.c_int
@@ -239,8 +242,12 @@ def ffa_bwd(
     q_ranges: torch.Tensor, k_ranges: torch.Tensor, attn_type_map: torch.Tensor | None,
     softmax_scale: float, softcap: float = 0.0, accumulate_dkv: bool = False, sm_margin: int = 0,
     sink: torch.Tensor | None = None, sink_layout: str = "sh", dsink: torch.Tensor | None = None,
+    row_stats: "BwdRowStats | None" = None,
 ) -> int:
-    """Enqueue the backward on the current stream (dq fp32 — and dsink when a sink is given — are accumulated into)."""
+    """Enqueue the backward on the current stream (dq fp32 — and dsink when a sink is given — are accumulated into).
+
+    `row_stats`: a BwdRowStats shared by the calls of ONE backward pass that use the same (out, dout, lse): the first call
+    fills it, the later ones skip the preprocess kernel."""
     l = lib()
     for t, n in ((dout, "dout"), (q, "q"), (k, "k"), (v, "v"), (out, "out"), (dq, "dq"), (dk, "dk"), (dv, "dv")):
         _req(t, n)
@@ -272,11 +279,36 @@ def ffa_bwd(
                 or dsink.device != q.device:
             raise RuntimeError("dsink must be a contiguous fp32 tensor shaped like sink")
         p.dsink = dsink.data_ptr()
+    if row_stats is not None:
+        p.row_stats, p.row_stats_ready = row_stats.bind(out, dout, lse), int(row_stats.ready)
     nbytes = l.b200_ffa_bwd_workspace_bytes(C.byref(p))
     ws = _workspace(nbytes, q.device)
     p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
     _check(l.b200_ffa_bwd(C.byref(p), _stream_ptr(q.device)), "b200_ffa_bwd")
+    if row_stats is not None and q.shape[0] > 0 and k.shape[0] > 0:
+        row_stats.ready = True
     return l.b200_ffa_last_launch_count()
+
+
+class BwdRowStats:
+    """The backward's per-(head, row) statistics (delta, lse * log2 e), kept between the stage calls of one pass.
+
+    Bound to the first (out, dout, lse) it sees; a call with different tensors is a programming error and raises."""
+
+    def __init__(self) -> None:
+        self.buf: torch.Tensor | None = None
+        self.ready = False
+        self._key: tuple | None = None
+
+    def bind(self, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor) -> int:
+        key = (out.data_ptr(), dout.data_ptr(), lse.data_ptr(), tuple(out.shape), torch.cuda.current_stream(out.device).cuda_stream)
+        if self._key is None:
+            self._key = key
+            n = lib().b200_ffa_bwd_row_stats_bytes(out.shape[0], out.shape[1])
+            self.buf = torch.empty(max(int(n), 256), dtype=torch.uint8, device=out.device)
+        elif key != self._key:
+            raise RuntimeError("BwdRowStats reused with different out / dout / lse tensors or on another stream")
+        return self.buf.data_ptr()
 
 
 def lse_merge(out: torch.Tensor, lse: torch.Tensor, out2: torch.Tensor, lse2: torch.Tensor) -> None:

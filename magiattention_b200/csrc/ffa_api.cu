@@ -187,6 +187,11 @@ size_t b200_ffa_bwd_workspace_bytes(const b200_ffa_bwd_params* p) {
   return plan + 2 * vec;
 }
 
+size_t b200_ffa_bwd_row_stats_bytes(int32_t total_q, int32_t num_heads_q) {
+  if (total_q < 0 || num_heads_q <= 0) return 0;
+  return 2 * align_up(size_t(num_heads_q) * bwd_tq_ld(total_q) * sizeof(float), 256);
+}
+
 int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream_) {
   g_err[0] = 0;
   g_launches = 0;
@@ -222,9 +227,12 @@ int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream_) {
   const size_t min_plan = align_up((ffa::plan_entries_off(n_tiles) + 1) * sizeof(int), 256);
   if (!p->workspace || (reinterpret_cast<uintptr_t>(p->workspace) & 255) || p->workspace_bytes < 2 * vec + min_plan)
     return fail(B200_ERR_WORKSPACE, "workspace too small (%zu < %zu) or not 256-byte aligned", p->workspace_bytes, need);
+  if (p->row_stats && (reinterpret_cast<uintptr_t>(p->row_stats) & 255)) return fail(B200_ERR_INVALID, "row_stats must be 256-byte aligned");
   char* ws = static_cast<char*>(p->workspace);
-  float* delta = reinterpret_cast<float*>(ws);
-  float* lse2 = reinterpret_cast<float*>(ws + vec);
+  char* stats = p->row_stats ? static_cast<char*>(p->row_stats) : ws;
+  float* delta = reinterpret_cast<float*>(stats);
+  float* lse2 = reinterpret_cast<float*>(stats + vec);
+  const bool stats_ready = p->row_stats && p->row_stats_ready;
   int* plan = reinterpret_cast<int*>(ws + 2 * vec);
   const size_t plan_bytes_avail = p->workspace_bytes - 2 * vec;
   const size_t cap = (plan_bytes_avail - ffa::plan_entries_off(n_tiles) * sizeof(int)) / sizeof(int);
@@ -235,11 +243,13 @@ int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream_) {
   cudaError_t e = ffa::launch_plan(false, meta, n_tiles, capacity, plan, stream);
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "plan launch: %s", cudaGetErrorString(e));
   ++g_launches;
-  e = ffa::launch_bwd_preprocess(p->head_dim, p->dtype == B200_BF16, p->out, p->dout, p->lse, delta, lse2, p->total_q, p->num_heads_q, tq_ld,
-                                 p->o_stride_t, p->o_stride_h, p->do_stride_t, p->do_stride_h, p->lse_stride_t, p->lse_stride_h,
-                                 stream);
-  if (e != cudaSuccess) return fail(B200_ERR_CUDA, "bwd preprocess launch: %s", cudaGetErrorString(e));
-  ++g_launches;
+  if (!stats_ready) {
+    e = ffa::launch_bwd_preprocess(p->head_dim, p->dtype == B200_BF16, p->out, p->dout, p->lse, delta, lse2, p->total_q, p->num_heads_q,
+                                   tq_ld, p->o_stride_t, p->o_stride_h, p->do_stride_t, p->do_stride_h, p->lse_stride_t,
+                                   p->lse_stride_h, stream);
+    if (e != cudaSuccess) return fail(B200_ERR_CUDA, "bwd preprocess launch: %s", cudaGetErrorString(e));
+    ++g_launches;
+  }
   if (p->sink && p->seqlen_sink > 0 && p->total_q > 0) {
     e = ffa::launch_sink_bwd(p->dsink, p->sink, p->lse, delta, p->total_q, p->num_heads_q, tq_ld, p->seqlen_sink, p->sink_layout,
                              p->lse_stride_t, p->lse_stride_h, stream);

@@ -216,10 +216,11 @@ class DistAttnRuntime:
                                  softmax_scale, softcap, torch.float32, sm_margin=self.sm_margin,
                                  return_max_logits=max_logits is not None, max_logits=max_logits)
 
-    def attn_bwd(self, do, q, k, v, out, lse, arg: AttnArg, dq_acc, dk, dv, softmax_scale, softcap, sink=None, dsink=None):
+    def attn_bwd(self, do, q, k, v, out, lse, arg: AttnArg, dq_acc, dk, dv, softmax_scale, softcap, sink=None, dsink=None,
+                 row_stats=None):
         a = self._ffa_args(arg, q.device)
         _flex_flash_attn_backward(do, q, k, v, sink, "sh", out, lse, dq_acc, dk, dv, dsink, a["q_ranges"], a["k_ranges"],
-                                  a["attn_type_map"], softmax_scale, softcap, sm_margin=self.sm_margin)
+                                  a["attn_type_map"], softmax_scale, softcap, sm_margin=self.sm_margin, row_stats=row_stats)
 
 
 class DistAttnFunc(torch.autograd.Function):
@@ -266,9 +267,12 @@ class DistAttnFunc(torch.autograd.Function):
         dk = torch.zeros(k.shape, dtype=torch.float32, device=k.device)
         dv = torch.zeros(v.shape, dtype=torch.float32, device=v.device)
         dsink = torch.zeros_like(sink, dtype=torch.float32) if sink is not None else None
+        # every stage call of this pass sees the same (out, dout, lse): their row statistics are computed once
+        row_stats = _lib.BwdRowStats()
         if not cm.local_attn_arg.can_skip or sink is not None:
             # the host stage also produces this rank's partial dsink (rows it owns; reference :663-713)
-            runtime.attn_bwd(dout, q, k, v, out, lse, cm.local_attn_arg, dq, dk, dv, scale, softcap, sink=sink, dsink=dsink)
+            runtime.attn_bwd(dout, q, k, v, out, lse, cm.local_attn_arg, dq, dk, dv, scale, softcap, sink=sink, dsink=dsink,
+                             row_stats=row_stats)
         wire = torch.float32 if runtime.high_precision_reduce else k.dtype
         runtime.mark_local_backward_done()
         reduces: list = []
@@ -288,7 +292,7 @@ class DistAttnFunc(torch.autograd.Function):
                 a = arg.to_ffa_args(q.device)
                 # fresh (non-accumulating) partial dk/dv in the wire dtype; dq accumulates
                 _lib.ffa_bwd(dout, q, rk, rv, out, lse, dq, dk_p, dv_p, a["q_ranges"], a["k_ranges"], a["attn_type_map"],
-                             scale, softcap, accumulate_dkv=False, sm_margin=runtime.sm_margin)
+                             scale, softcap, accumulate_dkv=False, sm_margin=runtime.sm_margin, row_stats=row_stats)
             reduces.append(runtime.reduce_partial_dkv(st, dk_p, dv_p, dk, dv, wire))
         runtime.begin_reduce(dk, dv, wire)
         runtime.finish_reduce(reduces)

@@ -129,6 +129,7 @@ def _flex_flash_attn_backward(
     disable_bwd_dkv_atomic_reduction: bool = False,
     deterministic: bool = False,
     sm_margin: int = 0,
+    row_stats: "_lib.BwdRowStats | None" = None,
     **unused,
 ) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor | None]:
     """Raw backward launcher.  ``out``/``lse`` are the GLOBAL forward results, so partial gradients over
@@ -157,7 +158,7 @@ def _flex_flash_attn_backward(
         dv = torch.empty_like(v, dtype=dv_type or torch.float32)
     _lib.ffa_bwd(dout, q, k, v, out, lse, dq, dk, dv, q_ranges, k_ranges, attn_type_map, softmax_scale, softcap,
                  accumulate_dkv=accumulate_dkv, sm_margin=sm_margin, sink=sink, sink_layout=sink_layout,
-                 dsink=dsink if sink is not None else None)
+                 dsink=dsink if sink is not None else None, row_stats=row_stats)
     return dq, dk, dv, (dsink if sink is not None else None)
 
 

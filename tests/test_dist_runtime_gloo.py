@@ -41,7 +41,7 @@ def _install_fake_kernels():
             dsink += orc.sink_bwd(sink, lse, out, do, sink_layout).to(dsink.dtype)
         return dq, dk, dv, dsink
 
-    def fake_lib_bwd(do, q, k, v, out, lse, dq, dk, dv, qr, kr, ty, scale, softcap=0.0, accumulate_dkv=False, sm_margin=0):
+    def fake_lib_bwd(do, q, k, v, out, lse, dq, dk, dv, qr, kr, ty, scale, softcap=0.0, accumulate_dkv=False, sm_margin=0, row_stats=None):
         a, b, c = _bwd(do, q, k, v, out, lse, qr, kr, ty, scale)
         dq += a.to(dq.dtype)
         dk.copy_(b); dv.copy_(c)

@@ -389,6 +389,24 @@ def test_backward_accumulates_dq_and_dkv():
     torch.testing.assert_close(dq2, dq, atol=2e-3, rtol=1e-3)
     torch.testing.assert_close(dk2, dk, atol=2e-3, rtol=1e-3)
     torch.testing.assert_close(dv2, dv, atol=2e-3, rtol=1e-3)
+    # the same two calls sharing one BwdRowStats (the second skips the preprocess kernel): bit-identical partial sums, one
+    # launch fewer, and the scratch workspace in between may be overwritten by another call
+    from magiattention_b200 import _lib
+
+    dq3, dk3, dv3 = torch.zeros_like(dq), torch.zeros_like(dk), torch.zeros_like(dv)
+    rs = _lib.BwdRowStats()
+    _flex_flash_attn_backward(do, q, k, v, None, "sh", out, meta.lse, dq3, dk3, dv3, None, qa, ka, ta, scale, 0.0, row_stats=rs)
+    n_first = _lib.lib().b200_ffa_last_launch_count()
+    assert rs.ready
+    _flex_flash_attn_forward(q, k, v, None, "sh", None, None, full_q, full_k, ty, scale, 0.0, None)  # clobbers the workspace
+    _flex_flash_attn_backward(do, q, k, v, None, "sh", out, meta.lse, dq3, dk3, dv3, None, qb, kb, tb, scale, 0.0, row_stats=rs)
+    assert _lib.lib().b200_ffa_last_launch_count() == n_first - 1
+    # dq is reduced with fp32 atomics in an unspecified order; dk / dv of disjoint calls are exact
+    torch.testing.assert_close(dq3, dq2, atol=1e-5, rtol=1e-5)
+    assert torch.equal(dk3, dk2) and torch.equal(dv3, dv2)
+    with pytest.raises(RuntimeError, match="BwdRowStats reused"):
+        _flex_flash_attn_backward(do.clone(), q, k, v, None, "sh", out, meta.lse, dq3, dk3, dv3, None, qb, kb, tb, scale, 0.0,
+                                  row_stats=rs)
 
 
 def test_error_behaviour():
