@@ -87,7 +87,9 @@ typedef struct {
    * functional/flex_flash_attn.py:334-456; the CP stage merge dist_attn.py:3126-3131).
    * accumulate == 0: out/lse are overwritten; uncovered rows get out = 0, lse = -inf. */
   int32_t accumulate;
-  int32_t sm_margin;           /* SMs to leave free for concurrent comm kernels */
+  int32_t sm_margin;           /* must be 0: the kernels are not persistent, every SM takes one CTA; a non-zero value is
+                                * rejected with B200_ERR_UNSUPPORTED instead of being ignored (reference: sm_margin,
+                                * flex_flash_attn.py:1103; env/comm.py:44-69) */
   void* workspace;             /* >= b200_ffa_fwd_workspace_bytes(), 256-byte aligned */
   size_t workspace_bytes;
   /* attention sink (NULL = none): `seqlen_sink` (<= 8, like the reference's kMaxSeqlenSink,

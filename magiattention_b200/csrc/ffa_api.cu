@@ -75,7 +75,8 @@ int make_map_f32_acc(CUtensorMap* m, void* ptr, int head_dim, int tokens, int he
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int check_common(int dtype, int hq, int hk, int d, float softcap) {
+int check_common(int dtype, int hq, int hk, int d, float softcap, int sm_margin) {
+  if (sm_margin != 0) return fail(B200_ERR_UNSUPPORTED, "sm_margin %d is not supported (must be 0)", sm_margin);
   if (dtype != B200_F16 && dtype != B200_BF16) return fail(B200_ERR_INVALID, "dtype must be f16 or bf16");
   if (d != 64 && d != 128) return fail(B200_ERR_UNSUPPORTED, "head_dim %d unsupported (only 64 and 128)", d);
   if (hq <= 0 || hk <= 0 || hq % hk) return fail(B200_ERR_INVALID, "num_heads_q %d must be a multiple of num_heads_kv %d", hq, hk);
@@ -109,7 +110,7 @@ int b200_ffa_fwd(const b200_ffa_fwd_params* p, b200_stream_t stream_) {
   g_launches = 0;
   if (!p) return fail(B200_ERR_INVALID, "null params");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (int rc = check_common(p->dtype, p->num_heads_q, p->num_heads_kv, p->head_dim, p->softcap)) return rc;
+  if (int rc = check_common(p->dtype, p->num_heads_q, p->num_heads_kv, p->head_dim, p->softcap, p->sm_margin)) return rc;
   if (p->out_dtype != p->dtype && p->out_dtype != B200_F32) return fail(B200_ERR_INVALID, "out_dtype must equal dtype or be f32");
   if (p->total_q < 0 || p->total_k < 0 || p->num_slices < 0) return fail(B200_ERR_INVALID, "negative size");
   if (p->total_q == 0) return 0;
@@ -197,7 +198,7 @@ int b200_ffa_bwd(const b200_ffa_bwd_params* p, b200_stream_t stream_) {
   g_launches = 0;
   if (!p) return fail(B200_ERR_INVALID, "null params");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (int rc = check_common(p->dtype, p->num_heads_q, p->num_heads_kv, p->head_dim, p->softcap)) return rc;
+  if (int rc = check_common(p->dtype, p->num_heads_q, p->num_heads_kv, p->head_dim, p->softcap, p->sm_margin)) return rc;
   if (p->dkv_dtype != p->dtype && p->dkv_dtype != B200_F32) return fail(B200_ERR_INVALID, "dkv_dtype must equal dtype or be f32");
   if (p->accumulate_dkv && p->dkv_dtype != B200_F32) return fail(B200_ERR_INVALID, "accumulate_dkv requires fp32 dk/dv");
   if (p->total_q < 0 || p->total_k < 0 || p->num_slices < 0) return fail(B200_ERR_INVALID, "negative size");

@@ -102,6 +102,9 @@ def test_argument_validation_needs_no_gpu(lib):
     p.num_heads_kv, p.softcap = 2, 1.0
     assert lib.b200_ffa_fwd(C.byref(p), None) == -4
     assert lib.b200_ffa_fwd(None, None) == -1
+    p.softcap, p.sm_margin = 0.0, 8
+    assert lib.b200_ffa_fwd(C.byref(p), None) == -4 and b"sm_margin" in lib.b200_ffa_last_error()
+    p.sm_margin = 0
     # sink / scale validation (fake non-null pointers: rejected before anything is dereferenced or launched)
     p.softcap, p.total_q, p.total_k, p.out_dtype = 0.0, 64, 64, _lib.B200_BF16
     p.q = p.k = p.v = p.out = p.lse = p.sink = 0x1000
