@@ -385,3 +385,51 @@ def test_api_surface_covers_reference_all():
 
     missing = [n for n in REFERENCE_API_ALL if not hasattr(alias, n) or not hasattr(ours, n)]
     assert not missing, missing
+
+
+@pytest.mark.parametrize("cfg,cp,degree", [("C3", 8, 4), ("C4", 8, 4), ("C5", 8, 4), ("C2", 4, 2)])
+def test_named_workloads_plan_at_full_size(cfg, cp, degree):
+    """The BASELINE configs at their FULL sizes (bench_workloads.py) through the planner, checked with size-independent
+    properties: the ranks' slices (local + every stage) conserve the mask area exactly, every stage slice addresses rows inside
+    its stage buffer, the stage buffers hold exactly the rows the transfer tables move, and the NVLink pull tables gather the
+    same global token ids as the naive group_cast (int64 ids, so a wrong row anywhere is a mismatch)."""
+    from bench_workloads import make_workload, slices_area
+    from magiattention_b200.comm.nvl_exchange import make_pull_plan, make_reduce_pull_plan
+
+    w = make_workload(cfg)
+    S = w["seq_len"]
+    sl = [(q_[0], q_[1], k_[0], k_[1], t) for q_, k_, t in zip(w["q_ranges"], w["k_ranges"], w["types"])]
+    chunk = 2048 if S >= 65536 else 512
+    assert S % (chunk * cp) == 0
+    dm = make_dispatch_meta(sl, S, chunk, cp)
+    comm, calc = make_attn_meta(sl, dm, degree)
+    area = 0
+    for r in range(cp):
+        args = [calc[r].local_attn_arg] + list(calc[r].remote_attn_args_list)
+        bounds = [dm.shard_seqlen] + [int(n) for n in comm[r].num_remote_kv_tokens_per_stage]
+        for a, kmax in zip(args, bounds):
+            qr, kr = list(a.q_ranges), list(a.k_ranges)
+            area += slices_area(qr, kr, list(a.attn_type_map))
+            assert slices_area(qr, kr, list(a.attn_type_map)) == a.total_area
+            assert all(0 <= q0 <= q1 <= dm.shard_seqlen for q0, q1 in qr)
+            assert all(0 <= k0 <= k1 <= kmax for k0, k1 in kr)
+    assert area == w["area"], (area, w["area"])
+    ids = [dm.position_ids(r).to(torch.int64) for r in range(cp)]
+    assert torch.equal(torch.sort(torch.cat(ids)).values, torch.arange(S))
+    for st in range(degree):
+        args = [comm[r].kv_group_collective_args_list[st] for r in range(cp)]
+        kw = dict(input_split_sizes=[a.input_split_size_list for a in args], dst_indices=[a.dst_indices_list for a in args],
+                  src_index=[a.src_index_list for a in args], output_split_sizes=[a.output_split_size_list for a in args])
+        want = orc.group_cast_ref([x[:, None] for x in ids], **kw)
+        for r in range(cp):
+            assert want[r].shape[0] == int(comm[r].num_remote_kv_tokens_per_stage[st])
+            got = torch.full((want[r].shape[0],), -1, dtype=torch.int64)
+            for (s, s0, d0, n) in make_pull_plan(args, r):
+                assert s != r
+                got[d0:d0 + n] = ids[s][s0:s0 + n]
+            assert torch.equal(got, want[r][:, 0])
+            # zero redundancy: a rank never fetches the same remote token twice in a stage
+            assert torch.unique(got).numel() == got.numel()
+            # the return path of the same stage lands every partial row on the owner's row of the same token
+            for (d, s0, l0, n) in make_reduce_pull_plan(args, r):
+                assert torch.equal(want[d][s0:s0 + n, 0], ids[r][l0:l0 + n])
