@@ -243,11 +243,16 @@ class NvlDomain:
         handles = [None] * self.world
         dist.all_gather_object(handles, _lib.nvl_export(self.base), group=self.group)
         self.peer_base = [self.base if r == self.rank else _lib.nvl_import(h) for r, h in enumerate(handles)]
-        self.view = torch.as_tensor(_RawCuda(self.base, total, self), device=self.device)
-        assert self.view.data_ptr() == self.base and self.view.device == self.device
+        self.view = self._map_view(total)
         self.pass_id = 0
         self.generation += 1
         dist.barrier(group=self.group)
+
+    def _map_view(self, total: int) -> torch.Tensor:
+        """This rank's arena as a uint8 tensor (no ownership: the arena outlives it)."""
+        v = torch.as_tensor(_RawCuda(self.base, total, self), device=self.device)
+        assert v.data_ptr() == self.base and v.device == self.device
+        return v
 
     def _release(self) -> None:
         if not self.base:
