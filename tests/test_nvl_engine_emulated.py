@@ -50,6 +50,21 @@ def test_nvl_engine_runtime_emulated_with_rank_skew(tmp_path):
     _run(4, _emu_body, str(tmp_path), [("causal", 2, False), ("varlen_block_causal_2k", 2, False), ("causal", 2, False)], 0.004)
 
 
+def _emu_sink_body(rank, world, shared_dir):
+    import nvl_emulation as emu
+    from test_dist_runtime_gloo import _sink_body
+
+    dom = emu.install(shared_dir, dist.group.WORLD)
+    _sink_body(rank, world, "causal", 2)
+    _sink_body(rank, world, "sliding_window_causal", 1)
+    assert dom.bytes_pulled > 0 and int(dom.err[0]) == 0
+
+
+def test_nvl_engine_sink_and_max_logits_emulated(tmp_path):
+    """Attention sink (applied once, on the host stage; partial dsink summed over the group) and max_logits on the NVLink engine."""
+    _run(2, _emu_sink_body, str(tmp_path))
+
+
 def _wrong_order_body(rank, world, shared_dir):
     import nvl_emulation as emu
     from magiattention_b200.comm import nvl_exchange as nx
